@@ -1,0 +1,72 @@
+// C-ABI entry for the tcgen05 GEMM (see include/mvlpt_sm100.h: mvlpt_gemm).
+#include "common.cuh"
+#include "gemm_sm100.cuh"
+
+using namespace mvlpt;
+
+template <int BN>
+static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const GemmEpilogue& ep,
+                       cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    CUtensorMap ta, tw;
+    {
+        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
+        uint64_t str[1] = {(uint64_t)d->lda * 2};
+        uint32_t box[2] = {(uint32_t)kGemmBK, (uint32_t)kGemmBM};
+        int rc = make_tmap_f16(&ta, A, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+        uint64_t str[1] = {(uint64_t)d->ldw * 2};
+        uint32_t box[2] = {(uint32_t)kGemmBK, (uint32_t)BN};
+        int rc = make_tmap_f16(&tw, W, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           Cfg::kSmemBytes));
+        attr_set = true;
+    }
+    const int tiles = cdiv(d->M, kGemmBM) * cdiv(d->N, BN);
+    const int grid = tiles < sm_count() ? tiles : sm_count();
+    gemm_f16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, d->M, d->N, d->K, ep);
+    return launched("gemm_f16_tn");
+}
+
+extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias,
+                          const void* aux_in, void* aux_out, const void* resid, void* out, mvlpt_stream_t stream) {
+    if (!d || !A || !W || !out) return fail(MVLPT_EINVAL, "mvlpt_gemm: null argument");
+    if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(MVLPT_EINVAL, "mvlpt_gemm: M,N,K must be positive");
+    if (d->lda < d->K || d->ldw < d->K || d->ld_out < d->N)
+        return fail(MVLPT_EINVAL, "mvlpt_gemm: leading dimension smaller than extent");
+    if ((d->lda % 8) || (d->ldw % 8)) return fail(MVLPT_ESHAPE, "mvlpt_gemm: lda/ldw must be multiples of 8");
+    if (d->out_f32 ? (d->ld_out % 4) : (d->ld_out % 8))
+        return fail(MVLPT_ESHAPE, "mvlpt_gemm: ld_out must be a multiple of %d", d->out_f32 ? 4 : 8);
+    if ((reinterpret_cast<uintptr_t>(out) & 15) || (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) ||
+        (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
+        return fail(MVLPT_EINVAL, "mvlpt_gemm: out/resid/bias must be 16-byte aligned");
+    if (d->act < 0 || d->act > 2) return fail(MVLPT_EINVAL, "mvlpt_gemm: unknown act %d", d->act);
+    if (d->act == ACT_MUL_DQUICKGELU && !aux_in) return fail(MVLPT_EINVAL, "mvlpt_gemm: act 2 needs aux_in");
+    if ((aux_in || aux_out) && (d->ld_aux < d->N || (d->ld_aux % 8)))
+        return fail(MVLPT_ESHAPE, "mvlpt_gemm: ld_aux must be >= N and a multiple of 8");
+    if (resid && !d->out_f32) return fail(MVLPT_ESHAPE, "mvlpt_gemm: the residual stream is fp32; set out_f32");
+    int rc = require_sm100();
+    if (rc) return rc;
+
+    GemmEpilogue ep;
+    ep.bias = static_cast<const __half*>(bias);
+    ep.aux_in = static_cast<const __half*>(aux_in);
+    ep.aux_out = static_cast<__half*>(aux_out);
+    ep.resid = static_cast<const float*>(resid);
+    ep.out = out;
+    ep.ld_out = d->ld_out;
+    ep.ld_aux = d->ld_aux;
+    ep.out_f32 = d->out_f32;
+    ep.act = d->act;
+    ep.alpha = d->alpha;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (d->N <= 128) return launch_gemm<128>(d, A, W, ep, s);
+    return launch_gemm<256>(d, A, W, ep, s);
+}
