@@ -62,6 +62,96 @@ typedef struct {
 int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* aux_in,
                void* aux_out, const void* resid, void* out, mvlpt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Attention core, head width 64 (d == heads*64), L <= 288, packed qkv [N*L, 3d] fp16 (Q | K | V).
+ * Replaces the inside of nn.MultiheadAttention (clip/model.py:171,181-183 -> F.multi_head_attention_forward:
+ * q*hd^-1/2, QK^T, causal -inf mask for the text tower clip/model.py:324-330, softmax, PV) and its autograd.
+ *   out  : fp16 [N*L, d]        lse : fp32 [N, heads, L]  (log-sum-exp of the scaled scores, saved for bwd)
+ *   dqkv : fp16 [N*L, 3d]       d_o : fp16 [N*L, d]
+ * ------------------------------------------------------------------------------------------------ */
+int mvlpt_fmha_fwd(const void* qkv, void* out, void* lse, int N, int L, int d, int heads, int causal,
+                   mvlpt_stream_t stream);
+int mvlpt_fmha_bwd(const void* qkv, const void* o, const void* d_o, const void* lse, void* dqkv, int N, int L, int d,
+                   int heads, int causal, mvlpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * LayerNorm with fp32 statistics (clip/model.py:153-159).  x: fp32 residual stream [*, d]; y: fp16 [rows, d].
+ * row_index (int32 [rows], may be NULL) gathers source rows: the CLS row (trainers/mvlpt.py:88) or the EOT
+ * row (trainers/mvlpt.py:124-128).  d % 4 == 0, d <= 1024.
+ * Backward (gamma/beta frozen, trainers/mvlpt.py:856-858): dx = rstd*(g - mean(g) - xhat*mean(g*xhat)),
+ * g = dy*gamma; written (accumulate=0) or added (accumulate=1) to the fp32 gradient stream at the same rows,
+ * with an optional fp16 copy dx16 of the result (operand of the next dgrad GEMM).
+ * ------------------------------------------------------------------------------------------------ */
+int mvlpt_ln_fwd(const void* x, const void* row_index, const void* gamma, const void* beta, void* y, int rows, int d,
+                 float eps, mvlpt_stream_t stream);
+int mvlpt_ln_bwd(const void* dy, const void* x, const void* row_index, const void* gamma, void* dx_stream, void* dx16,
+                 int rows, int d, float eps, int accumulate, mvlpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Image stem (trainers/mvlpt.py:53-58 = clip/model.py:220-225; conv1 clip/model.py:207).
+ * mvlpt_im2col: img [B,3,H,W] (fp16, or fp32 when img_f32) -> patches fp16 [B*(H/p)*(W/p), Kp],
+ *   column c*p*p + ky*p + kx (the conv weight's own flattening), columns [3pp, Kp) zero; Kp % 8 == 0.
+ *   The conv itself is then mvlpt_gemm against conv1.weight viewed as [d, Kp].
+ * mvlpt_embed_assemble: x0[b,0] = ln_pre(cls + pos[0]); x0[b,1..v] = prompt[0..v) (forward_vpt,
+ *   trainers/mvlpt.py:416-437: prompts get neither pos-emb nor ln_pre); x0[b,1+v+i] = ln_pre(pe[b,i] + pos[1+i]).
+ *   pe fp16 [B*G, d]; cls/pos/gamma/beta fp32; prompt fp16 or fp32 [v, d]; x0 fp32 [B, 1+v+G, d].
+ * mvlpt_set_prompt_rows: x[b,1+j] = prompt[j] — the deep-prompt replacement before block l>=1
+ *   (trainers/mvlpt.py:73-82).
+ * mvlpt_prompt_grad: grad[j] = inv_scale * sum_b dx[b,1+j] (autograd of the expand over B); with zero_rows the
+ *   rows are then cleared in dx (and dx16) because the replaced rows have no upstream.
+ * ------------------------------------------------------------------------------------------------ */
+int mvlpt_im2col(const void* img, int img_f32, void* patches, int B, int H, int W, int p, int Kp, mvlpt_stream_t stream);
+int mvlpt_embed_assemble(const void* pe, const void* cls, const void* pos, const void* gamma, const void* beta,
+                         const void* prompt, int prompt_f16, void* x0, int B, int G, int v, int d, float eps,
+                         mvlpt_stream_t stream);
+int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d,
+                          mvlpt_stream_t stream);
+int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int d, float inv_scale, int zero_rows,
+                      mvlpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Text prompt assembly (forward_coop, trainers/mvlpt.py:439-515, fused with `+ positional_embedding`,
+ * trainers/mvlpt.py:107/112).  emb fp32 [C, Lt, d] = token_embedding(tokenised "X .. X name.");
+ * slot int32 [C, Lt]: >= 0 selects context vector `slot` (of class c when csc), -1 keeps emb.  The map encodes
+ * end / middle / front placement, so no per-class Python loop is needed.  ctx NULL = fixed prompt.
+ * mvlpt_ctx_grad: grad[j] = inv_scale * sum_c dx0[c, ctx_pos[c,j]]  (or per class when csc); ctx_pos int32 [C,n].
+ * ------------------------------------------------------------------------------------------------ */
+int mvlpt_text_assemble(const void* emb, const void* ctx, int ctx_f16, const void* slot, const void* pos, void* x0,
+                        int C, int Lt, int n_ctx, int d, int csc, mvlpt_stream_t stream);
+int mvlpt_ctx_grad(const void* dx0, const void* ctx_pos, void* grad, int C, int Lt, int n_ctx, int d, int csc,
+                   float inv_scale, mvlpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Logit head (trainers/mvlpt.py:550-554, 573-581) and loss (trainers/mvlpt.py:914-916, 922/931).
+ * mvlpt_l2norm_fwd: y = x/||x|| per row; x fp32 [rows,e] -> y16 fp16, y32 fp32, inv_norm fp32 [rows].
+ * mvlpt_l2norm_bwd: dx16 = (dy - y (y.dy)) * inv_norm.
+ * mvlpt_ce_fwd_bwd: logits fp32 [B, ldc] (C valid columns) are first multiplied in place by the task mask
+ *   (task int32 [B], ranges int32 [T,2]; NULL = no mask), then loss_rows[b] = CE(row, target) with integer
+ *   labels (int64 [B]) or soft targets (fp32 [B,C], rows normalised to sum 1 inside); pred[b] = argmax;
+ *   dz16 fp16 [B, ldc] = coef * (softmax - y) * mask (may be NULL for evaluation).
+ * mvlpt_dlogits_prepare: dz16 = coef * dlogits * mask, for callers that compute their own loss (autograd).
+ * mvlpt_transpose_f16: out[c,r] = in[r,c], zero padded to ld_out — operand layout for the head dgrads.
+ * ------------------------------------------------------------------------------------------------ */
+int mvlpt_l2norm_fwd(const void* x, void* y16, void* y32, void* inv_norm, int rows, int e, mvlpt_stream_t stream);
+int mvlpt_l2norm_bwd(const void* dy, const void* y32, const void* inv_norm, void* dx16, int rows, int e,
+                     mvlpt_stream_t stream);
+int mvlpt_ce_fwd_bwd(void* logits, int ldc, const void* label, const void* soft, const void* task, const void* ranges,
+                     void* loss_rows, void* pred, void* dz16, int B, int C, float coef, mvlpt_stream_t stream);
+int mvlpt_dlogits_prepare(const void* dlogits, int ld_in, const void* task, const void* ranges, void* dz16, int ldc,
+                          int B, int C, float coef, mvlpt_stream_t stream);
+int mvlpt_transpose_f16(const void* in, void* out, int R, int Cc, int ld_in, int ld_out, mvlpt_stream_t stream);
+/* logits[b,c] *= 1[ranges[task[b]][0] <= c < ranges[task[b]][1]]  (trainers/mvlpt.py:573-581; multiplies by 0) */
+int mvlpt_task_mask(void* logits, int ldc, const void* task, const void* ranges, int B, int C, mvlpt_stream_t stream);
+
+/* SGD with momentum + L2 weight decay on one prompt tensor (torch.optim.SGD as Dassl builds it for
+ * trainers/mvlpt.py:869: g += wd*p; buf = mu*buf + g (buf = g on the first step); p -= lr*buf).
+ * p/buf: fp16 (is_f16) or fp32; g: fp32 unscaled gradient. */
+int mvlpt_sgd(void* p, void* buf, const void* g, int n, int is_f16, float lr, float momentum, float wd, int first_step,
+              mvlpt_stream_t stream);
+
+/* cudaMemsetAsync(p, 0, bytes) on the stream. */
+int mvlpt_zero(void* p, size_t bytes, mvlpt_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -40,18 +40,13 @@ def lib() -> ctypes.CDLL:
                 f"{LIB_PATH} is missing: build it with `python -m mvlpt_b200.build` "
                 "(or __graft_entry__.build()). There is no CPU fallback.")
     L = ctypes.CDLL(str(LIB_PATH))
-    L.mvlpt_version.restype = c_int
-    L.mvlpt_last_error.restype = c_char_p
-    L.mvlpt_launch_count.restype = c_uint64
-    L.mvlpt_check_device.argtypes = [c_int]
-    L.mvlpt_gemm.argtypes = [POINTER(GemmDesc)] + [c_void_p] * 8
     _declare_ops(L)
     _lib = L
     return L
 
 
 def _declare_ops(L):
-    """argtypes for the non-GEMM entry points (filled in by ops.py's descriptor table)."""
+    """argtypes/restype for every entry point, parsed from include/mvlpt_sm100.h."""
     from . import _abi
     _abi.declare(L)
 

@@ -1,0 +1,419 @@
+// HBM-bound row kernels of the hot path: LayerNorm forward/backward (fp32 statistics, clip/model.py:153-159),
+// patch gather (im2col of the stride-p conv, clip/model.py:207), token assembly for both towers
+// (trainers/mvlpt.py:53-58,416-437,455-510), deep-prompt row replacement (trainers/mvlpt.py:73-82) and the
+// batch reductions that turn activation gradients into prompt gradients.
+// One warp per row, 128-bit accesses, rows kept in registers (d <= 1024).
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+using namespace mvlpt;
+
+namespace {
+
+constexpr int kMaxV4 = 8;  // d <= 8 * 128
+
+__device__ __forceinline__ float wsum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+struct Row {
+    float4 v[kMaxV4];
+};
+
+__device__ __forceinline__ void row_load(Row& r, const float* p, int d, int lane) {
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const int c = i * 128 + lane * 4;
+        r.v[i] = (c < d) ? *reinterpret_cast<const float4*>(p + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+__device__ __forceinline__ void row_load_h(Row& r, const __half* p, int d, int lane) {
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < d) {
+            const uint2 u = *reinterpret_cast<const uint2*>(p + c);
+            const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+            const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            r.v[i] = make_float4(a.x, a.y, b.x, b.y);
+        } else {
+            r.v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+    }
+}
+__device__ __forceinline__ void row_store(const Row& r, float* p, int d, int lane) {
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < d) *reinterpret_cast<float4*>(p + c) = r.v[i];
+    }
+}
+__device__ __forceinline__ void row_store_h(const Row& r, __half* p, int d, int lane) {
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < d) {
+            uint2 u;
+            *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(r.v[i].x, r.v[i].y);
+            *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(r.v[i].z, r.v[i].w);
+            *reinterpret_cast<uint2*>(p + c) = u;
+        }
+    }
+}
+// mean / rstd of a row held in registers (two-pass, biased variance)
+__device__ __forceinline__ void row_stats(const Row& r, int d, int lane, float eps, float& mean, float& rstd) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) s += r.v[i].x + r.v[i].y + r.v[i].z + r.v[i].w;  // padding lanes hold 0
+    mean = wsum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < d) {
+            const float a = r.v[i].x - mean, b = r.v[i].y - mean, e = r.v[i].z - mean, f = r.v[i].w - mean;
+            q += a * a + b * b + e * e + f * f;
+        }
+    }
+    rstd = rsqrtf(wsum(q) / d + eps);
+}
+__device__ __forceinline__ void row_affine(Row& r, const float* g, const float* b, int d, int lane, float mean,
+                                           float rstd) {
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < d) {
+            const float4 gg = *reinterpret_cast<const float4*>(g + c);
+            const float4 bb = *reinterpret_cast<const float4*>(b + c);
+            r.v[i].x = (r.v[i].x - mean) * rstd * gg.x + bb.x;
+            r.v[i].y = (r.v[i].y - mean) * rstd * gg.y + bb.y;
+            r.v[i].z = (r.v[i].z - mean) * rstd * gg.z + bb.z;
+            r.v[i].w = (r.v[i].w - mean) * rstd * gg.w + bb.w;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- LayerNorm forward
+__global__ void ln_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_index,
+                              const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
+                              int rows, int d, float eps) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const size_t src = row_index ? (size_t)row_index[r] : (size_t)r;
+    Row row;
+    row_load(row, x + src * d, d, lane);
+    float mean, rstd;
+    row_stats(row, d, lane, eps, mean, rstd);
+    row_affine(row, gamma, beta, d, lane, mean, rstd);
+    row_store_h(row, y + (size_t)r * d, d, lane);
+}
+
+// ---------------------------------------------------------------- LayerNorm backward (gamma/beta frozen)
+// g = dy*gamma ; dx = rstd * (g - mean(g) - xhat*mean(g*xhat))
+__global__ void ln_bwd_kernel(const __half* __restrict__ dy, const float* __restrict__ x,
+                              const int* __restrict__ row_index, const float* __restrict__ gamma,
+                              float* __restrict__ dx_stream, __half* __restrict__ dx16, int rows, int d, float eps,
+                              int accumulate) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const size_t dst = row_index ? (size_t)row_index[r] : (size_t)r;
+    Row xr, g;
+    row_load(xr, x + dst * d, d, lane);
+    float mean, rstd;
+    row_stats(xr, d, lane, eps, mean, rstd);
+    row_load_h(g, dy + (size_t)r * d, d, lane);
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < d) {
+            const float4 gg = *reinterpret_cast<const float4*>(gamma + c);
+            g.v[i].x *= gg.x; g.v[i].y *= gg.y; g.v[i].z *= gg.z; g.v[i].w *= gg.w;
+            xr.v[i].x = (xr.v[i].x - mean) * rstd; xr.v[i].y = (xr.v[i].y - mean) * rstd;
+            xr.v[i].z = (xr.v[i].z - mean) * rstd; xr.v[i].w = (xr.v[i].w - mean) * rstd;
+            s1 += g.v[i].x + g.v[i].y + g.v[i].z + g.v[i].w;
+            s2 += g.v[i].x * xr.v[i].x + g.v[i].y * xr.v[i].y + g.v[i].z * xr.v[i].z + g.v[i].w * xr.v[i].w;
+        }
+    }
+    s1 = wsum(s1) / d;
+    s2 = wsum(s2) / d;
+    Row out;
+    if (accumulate) row_load(out, dx_stream + dst * d, d, lane);
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const float4 a = g.v[i], h = xr.v[i];
+        float4 o = make_float4(rstd * (a.x - s1 - h.x * s2), rstd * (a.y - s1 - h.y * s2), rstd * (a.z - s1 - h.z * s2),
+                               rstd * (a.w - s1 - h.w * s2));
+        if (accumulate) { o.x += out.v[i].x; o.y += out.v[i].y; o.z += out.v[i].z; o.w += out.v[i].w; }
+        out.v[i] = o;
+    }
+    row_store(out, dx_stream + dst * d, d, lane);
+    if (dx16) row_store_h(out, dx16 + dst * d, d, lane);
+}
+
+// ---------------------------------------------------------------- im2col for the patch-embedding conv
+// patches[(b*g + py)*g + px, c*p*p + ky*p + kx] = img[b, c, py*p+ky, px*p+kx]; columns [3pp, Kp) are zero.
+template <typename T>
+__global__ void im2col_kernel(const T* __restrict__ img, __half* __restrict__ patches, int B, int H, int W, int p, int Kp) {
+    const int g = W / p, gh = H / p;
+    const int patch = blockIdx.x;  // b*gh*g + py*g + px
+    const int b = patch / (gh * g), rem = patch % (gh * g), py = rem / g, px = rem % g;
+    __half* dst = patches + (size_t)patch * Kp;
+    const int K = 3 * p * p;
+    for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
+        float v = 0.f;
+        if (k < K) {
+            const int c = k / (p * p), r2 = k % (p * p), ky = r2 / p, kx = r2 % p;
+            v = (float)img[(((size_t)b * 3 + c) * H + py * p + ky) * W + px * p + kx];
+        }
+        dst[k] = __float2half_rn(v);
+    }
+}
+
+// ---------------------------------------------------------------- image token assembly
+// x0[b,0] = LNpre(cls + pos[0]); x0[b,1..v] = prompt; x0[b,1+v+i] = LNpre(pe[b,i] + pos[1+i])
+__global__ void embed_assemble_kernel(const __half* __restrict__ pe, const float* __restrict__ cls,
+                                      const float* __restrict__ pos, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const void* __restrict__ prompt, int prompt_f16,
+                                      float* __restrict__ x0, int B, int G, int v, int d, float eps) {
+    const int L = 1 + v + G;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= B * L) return;
+    const int b = r / L, t = r % L;
+    Row row;
+    if (t >= 1 && t <= v) {
+        if (prompt_f16) row_load_h(row, static_cast<const __half*>(prompt) + (size_t)(t - 1) * d, d, lane);
+        else row_load(row, static_cast<const float*>(prompt) + (size_t)(t - 1) * d, d, lane);
+    } else {
+        Row p;
+        const int pi = (t == 0) ? 0 : t - v;
+        if (t == 0) row_load(row, cls, d, lane);
+        else row_load_h(row, pe + ((size_t)b * G + (t - 1 - v)) * d, d, lane);
+        row_load(p, pos + (size_t)pi * d, d, lane);
+#pragma unroll
+        for (int i = 0; i < kMaxV4; ++i) {
+            row.v[i].x += p.v[i].x; row.v[i].y += p.v[i].y; row.v[i].z += p.v[i].z; row.v[i].w += p.v[i].w;
+        }
+        float mean, rstd;
+        row_stats(row, d, lane, eps, mean, rstd);
+        row_affine(row, gamma, beta, d, lane, mean, rstd);
+    }
+    row_store(row, x0 + (size_t)r * d, d, lane);
+}
+
+// x[b, 1+j] = prompt[j]  (deep prompt replacement before block l >= 1)
+__global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __restrict__ prompt, int prompt_f16, int B,
+                                       int L, int v, int d) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= B * v) return;
+    const int b = r / v, j = r % v;
+    Row row;
+    if (prompt_f16) row_load_h(row, static_cast<const __half*>(prompt) + (size_t)j * d, d, lane);
+    else row_load(row, static_cast<const float*>(prompt) + (size_t)j * d, d, lane);
+    row_store(row, x + ((size_t)b * L + 1 + j) * d, d, lane);
+}
+
+// grad[j, :] = inv_scale * sum_b dx[b, 1+j, :]; optionally zero those rows (they do not flow further back)
+__global__ void prompt_grad_kernel(float* __restrict__ dx, __half* __restrict__ dx16, float* __restrict__ grad, int B,
+                                   int L, int v, int d, float inv_scale, int zero_rows) {
+    const int j = blockIdx.y;
+    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (c >= d) return;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int b = 0; b < B; ++b) {
+        float* p = dx + ((size_t)b * L + 1 + j) * d + c;
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+        if (zero_rows) {
+            *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dx16) *reinterpret_cast<uint2*>(dx16 + ((size_t)b * L + 1 + j) * d + c) = make_uint2(0u, 0u);
+        }
+    }
+    *reinterpret_cast<float4*>(grad + (size_t)j * d + c) =
+        make_float4(acc.x * inv_scale, acc.y * inv_scale, acc.z * inv_scale, acc.w * inv_scale);
+}
+
+// ---------------------------------------------------------------- text token assembly
+// x0[c,t] = (slot[c,t] >= 0 ? ctx[(csc ? c*n : 0) + slot[c,t]] : emb[c,t]) + pos[t]
+__global__ void text_assemble_kernel(const float* __restrict__ emb, const void* __restrict__ ctx, int ctx_f16,
+                                     const int* __restrict__ slot, const float* __restrict__ pos, float* __restrict__ x0,
+                                     int C, int Lt, int n_ctx, int d, int csc) {
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= C * Lt) return;
+    const int c = r / Lt, t = r % Lt;
+    const int s = (ctx != nullptr) ? slot[r] : -1;
+    Row row, p;
+    if (s >= 0) {
+        const size_t off = ((size_t)(csc ? c * n_ctx : 0) + s) * d;
+        if (ctx_f16) row_load_h(row, static_cast<const __half*>(ctx) + off, d, lane);
+        else row_load(row, static_cast<const float*>(ctx) + off, d, lane);
+    } else {
+        row_load(row, emb + (size_t)r * d, d, lane);
+    }
+    row_load(p, pos + (size_t)t * d, d, lane);
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        row.v[i].x += p.v[i].x; row.v[i].y += p.v[i].y; row.v[i].z += p.v[i].z; row.v[i].w += p.v[i].w;
+    }
+    row_store(row, x0 + (size_t)r * d, d, lane);
+}
+
+// grad_ctx[j] = inv_scale * sum_c dx0[c, ctx_pos[c,j]]   (shared context)   or per class when csc
+__global__ void ctx_grad_kernel(const float* __restrict__ dx0, const int* __restrict__ ctx_pos, float* __restrict__ grad,
+                                int C, int Lt, int n_ctx, int d, int csc, float inv_scale) {
+    const int j = blockIdx.y;
+    const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (col >= d) return;
+    if (csc) {
+        const int c = blockIdx.z;
+        const float4 t = *reinterpret_cast<const float4*>(dx0 + ((size_t)c * Lt + ctx_pos[c * n_ctx + j]) * d + col);
+        *reinterpret_cast<float4*>(grad + ((size_t)c * n_ctx + j) * d + col) =
+            make_float4(t.x * inv_scale, t.y * inv_scale, t.z * inv_scale, t.w * inv_scale);
+        return;
+    }
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int c = 0; c < C; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(dx0 + ((size_t)c * Lt + ctx_pos[c * n_ctx + j]) * d + col);
+        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+    }
+    *reinterpret_cast<float4*>(grad + (size_t)j * d + col) =
+        make_float4(acc.x * inv_scale, acc.y * inv_scale, acc.z * inv_scale, acc.w * inv_scale);
+}
+
+inline int check_d(int d, const char* who) {
+    if (d <= 0 || d > kMaxV4 * 128 || (d % 4)) return fail(MVLPT_ESHAPE, "%s: d=%d must be a multiple of 4, <= 1024", who, d);
+    return MVLPT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mvlpt_ln_fwd(const void* x, const void* row_index, const void* gamma, const void* beta, void* y, int rows, int d,
+                 float eps, mvlpt_stream_t stream) {
+    if (!x || !gamma || !beta || !y) return fail(MVLPT_EINVAL, "mvlpt_ln_fwd: null argument");
+    if (rows <= 0) return fail(MVLPT_EINVAL, "mvlpt_ln_fwd: rows must be positive");
+    int rc = check_d(d, "mvlpt_ln_fwd");
+    if (rc) return rc;
+    if ((rc = require_sm100())) return rc;
+    ln_fwd_kernel<<<cdiv(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(x), static_cast<const int*>(row_index), static_cast<const float*>(gamma),
+        static_cast<const float*>(beta), static_cast<__half*>(y), rows, d, eps);
+    return launched("ln_fwd");
+}
+
+int mvlpt_ln_bwd(const void* dy, const void* x, const void* row_index, const void* gamma, void* dx_stream, void* dx16,
+                 int rows, int d, float eps, int accumulate, mvlpt_stream_t stream) {
+    if (!dy || !x || !gamma || !dx_stream) return fail(MVLPT_EINVAL, "mvlpt_ln_bwd: null argument");
+    if (rows <= 0) return fail(MVLPT_EINVAL, "mvlpt_ln_bwd: rows must be positive");
+    int rc = check_d(d, "mvlpt_ln_bwd");
+    if (rc) return rc;
+    if ((rc = require_sm100())) return rc;
+    ln_bwd_kernel<<<cdiv(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(dy), static_cast<const float*>(x), static_cast<const int*>(row_index),
+        static_cast<const float*>(gamma), static_cast<float*>(dx_stream), static_cast<__half*>(dx16), rows, d, eps,
+        accumulate);
+    return launched("ln_bwd");
+}
+
+int mvlpt_im2col(const void* img, int img_f32, void* patches, int B, int H, int W, int p, int Kp,
+                 mvlpt_stream_t stream) {
+    if (!img || !patches) return fail(MVLPT_EINVAL, "mvlpt_im2col: null argument");
+    if (B <= 0 || p <= 0 || H % p || W % p || Kp < 3 * p * p || (Kp % 8))
+        return fail(MVLPT_ESHAPE, "mvlpt_im2col: bad shape B=%d H=%d W=%d p=%d Kp=%d", B, H, W, p, Kp);
+    int rc = require_sm100();
+    if (rc) return rc;
+    const int patches_n = B * (H / p) * (W / p);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (img_f32)
+        im2col_kernel<float><<<patches_n, 256, 0, s>>>(static_cast<const float*>(img), static_cast<__half*>(patches), B,
+                                                       H, W, p, Kp);
+    else
+        im2col_kernel<__half><<<patches_n, 256, 0, s>>>(static_cast<const __half*>(img), static_cast<__half*>(patches),
+                                                        B, H, W, p, Kp);
+    return launched("im2col");
+}
+
+int mvlpt_embed_assemble(const void* pe, const void* cls, const void* pos, const void* gamma, const void* beta,
+                         const void* prompt, int prompt_f16, void* x0, int B, int G, int v, int d, float eps,
+                         mvlpt_stream_t stream) {
+    if (!pe || !cls || !pos || !gamma || !beta || !x0 || (v > 0 && !prompt))
+        return fail(MVLPT_EINVAL, "mvlpt_embed_assemble: null argument");
+    if (B <= 0 || G <= 0 || v < 0) return fail(MVLPT_EINVAL, "mvlpt_embed_assemble: bad sizes");
+    int rc = check_d(d, "mvlpt_embed_assemble");
+    if (rc) return rc;
+    if ((rc = require_sm100())) return rc;
+    const int rows = B * (1 + v + G);
+    embed_assemble_kernel<<<cdiv(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const __half*>(pe), static_cast<const float*>(cls), static_cast<const float*>(pos),
+        static_cast<const float*>(gamma), static_cast<const float*>(beta), prompt, prompt_f16,
+        static_cast<float*>(x0), B, G, v, d, eps);
+    return launched("embed_assemble");
+}
+
+int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d,
+                          mvlpt_stream_t stream) {
+    if (!x || !prompt) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows: null argument");
+    if (B <= 0 || v <= 0 || L < 1 + v) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows: bad sizes");
+    int rc = check_d(d, "mvlpt_set_prompt_rows");
+    if (rc) return rc;
+    if ((rc = require_sm100())) return rc;
+    set_prompt_rows_kernel<<<cdiv(B * v, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<float*>(x), prompt, prompt_f16, B, L, v, d);
+    return launched("set_prompt_rows");
+}
+
+int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int d, float inv_scale, int zero_rows,
+                      mvlpt_stream_t stream) {
+    if (!dx || !grad) return fail(MVLPT_EINVAL, "mvlpt_prompt_grad: null argument");
+    if (B <= 0 || v <= 0 || L < 1 + v) return fail(MVLPT_EINVAL, "mvlpt_prompt_grad: bad sizes");
+    int rc = check_d(d, "mvlpt_prompt_grad");
+    if (rc) return rc;
+    if ((rc = require_sm100())) return rc;
+    dim3 grid(cdiv(d / 4, 64), v);
+    prompt_grad_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<float*>(dx), static_cast<__half*>(dx16), static_cast<float*>(grad), B, L, v, d, inv_scale, zero_rows);
+    return launched("prompt_grad");
+}
+
+int mvlpt_text_assemble(const void* emb, const void* ctx, int ctx_f16, const void* slot, const void* pos, void* x0,
+                        int C, int Lt, int n_ctx, int d, int csc, mvlpt_stream_t stream) {
+    if (!emb || !pos || !x0 || (ctx && !slot)) return fail(MVLPT_EINVAL, "mvlpt_text_assemble: null argument");
+    if (C <= 0 || Lt <= 0) return fail(MVLPT_EINVAL, "mvlpt_text_assemble: bad sizes");
+    int rc = check_d(d, "mvlpt_text_assemble");
+    if (rc) return rc;
+    if ((rc = require_sm100())) return rc;
+    text_assemble_kernel<<<cdiv(C * Lt, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(emb), ctx, ctx_f16, static_cast<const int*>(slot), static_cast<const float*>(pos),
+        static_cast<float*>(x0), C, Lt, n_ctx, d, csc);
+    return launched("text_assemble");
+}
+
+int mvlpt_ctx_grad(const void* dx0, const void* ctx_pos, void* grad, int C, int Lt, int n_ctx, int d, int csc,
+                   float inv_scale, mvlpt_stream_t stream) {
+    if (!dx0 || !ctx_pos || !grad) return fail(MVLPT_EINVAL, "mvlpt_ctx_grad: null argument");
+    if (C <= 0 || Lt <= 0 || n_ctx <= 0) return fail(MVLPT_EINVAL, "mvlpt_ctx_grad: bad sizes");
+    int rc = check_d(d, "mvlpt_ctx_grad");
+    if (rc) return rc;
+    if ((rc = require_sm100())) return rc;
+    dim3 grid(cdiv(d / 4, 64), n_ctx, csc ? C : 1);
+    ctx_grad_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(dx0), static_cast<const int*>(ctx_pos), static_cast<float*>(grad), C, Lt, n_ctx, d,
+        csc, inv_scale);
+    return launched("ctx_grad");
+}
+
+int mvlpt_zero(void* p, size_t bytes, mvlpt_stream_t stream) {
+    if (!p) return fail(MVLPT_EINVAL, "mvlpt_zero: null argument");
+    MVLPT_CUDA_OK(cudaMemsetAsync(p, 0, bytes, static_cast<cudaStream_t>(stream)));
+    return MVLPT_OK;
+}
+
+}  // extern "C"

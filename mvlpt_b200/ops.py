@@ -1,0 +1,140 @@
+"""Tensor-level wrappers over the C ABI: pointer extraction + shape/dtype checks, nothing else.
+
+torch is used here only as the owner of device memory and streams; every function launches kernels from
+libmvlpt_sm100.so on the current CUDA stream and raises MvlptError on failure (no fallback).
+"""
+from __future__ import annotations
+
+import ctypes
+from ctypes import byref
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import GemmDesc, check
+
+ACT_NONE, ACT_QUICKGELU, ACT_MUL_DQUICKGELU = 0, 1, 2
+LN_EPS = 1e-5
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _chk(t: torch.Tensor, dtype, name: str):
+    if t.dtype != dtype or not t.is_cuda or not t.is_contiguous():
+        raise _lib.MvlptError(f"{name}: expected contiguous CUDA {dtype}, got {t.dtype} cuda={t.is_cuda} "
+                              f"contig={t.is_contiguous()}")
+
+
+def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid=None, alpha=1.0,
+         M=None, N=None, K=None, lda=None, ldw=None, ld_out=None, ld_aux=None):
+    """out[M,N] = epi(alpha * A[M,K] @ W[N,K]^T); see include/mvlpt_sm100.h:mvlpt_gemm."""
+    _chk(A, torch.float16, "gemm A")
+    _chk(W, torch.float16, "gemm W")
+    M = A.shape[0] if M is None else M
+    K = A.shape[1] if K is None else K
+    N = W.shape[0] if N is None else N
+    lda = A.stride(0) if lda is None else lda
+    ldw = W.stride(0) if ldw is None else ldw
+    ld_out = out.stride(0) if ld_out is None else ld_out
+    aux = aux_in if aux_in is not None else aux_out
+    ld_aux = (aux.stride(0) if aux is not None else 0) if ld_aux is None else ld_aux
+    out_f32 = int(out.dtype == torch.float32)
+    if not out_f32 and out.dtype != torch.float16:
+        raise _lib.MvlptError("gemm out must be fp16 or fp32")
+    d = GemmDesc(M, N, K, lda, ldw, ld_out, ld_aux, act, out_f32, float(alpha))
+    check(_lib.lib().mvlpt_gemm(byref(d), _p(A), _p(W), _p(bias), _p(aux_in), _p(aux_out), _p(resid), _p(out),
+                                _stream()), "mvlpt_gemm")
+    return out
+
+
+def fmha_fwd(qkv, out, lse, N, L, d, heads, causal):
+    check(_lib.lib().mvlpt_fmha_fwd(_p(qkv), _p(out), _p(lse), N, L, d, heads, int(causal), _stream()), "mvlpt_fmha_fwd")
+
+
+def fmha_bwd(qkv, o, d_o, lse, dqkv, N, L, d, heads, causal):
+    check(_lib.lib().mvlpt_fmha_bwd(_p(qkv), _p(o), _p(d_o), _p(lse), _p(dqkv), N, L, d, heads, int(causal), _stream()),
+          "mvlpt_fmha_bwd")
+
+
+def ln_fwd(x, gamma, beta, y, rows, d, row_index=None):
+    check(_lib.lib().mvlpt_ln_fwd(_p(x), _p(row_index), _p(gamma), _p(beta), _p(y), rows, d, LN_EPS, _stream()),
+          "mvlpt_ln_fwd")
+
+
+def ln_bwd(dy, x, gamma, dx_stream, dx16, rows, d, accumulate, row_index=None):
+    check(_lib.lib().mvlpt_ln_bwd(_p(dy), _p(x), _p(row_index), _p(gamma), _p(dx_stream), _p(dx16), rows, d, LN_EPS,
+                                  int(accumulate), _stream()), "mvlpt_ln_bwd")
+
+
+def im2col(img, patches, B, H, W, p, Kp):
+    check(_lib.lib().mvlpt_im2col(_p(img), int(img.dtype == torch.float32), _p(patches), B, H, W, p, Kp, _stream()),
+          "mvlpt_im2col")
+
+
+def embed_assemble(pe, cls, pos, gamma, beta, prompt, x0, B, G, v, d):
+    f16 = int(prompt is not None and prompt.dtype == torch.float16)
+    check(_lib.lib().mvlpt_embed_assemble(_p(pe), _p(cls), _p(pos), _p(gamma), _p(beta), _p(prompt), f16, _p(x0), B, G,
+                                          v, d, LN_EPS, _stream()), "mvlpt_embed_assemble")
+
+
+def set_prompt_rows(x, prompt, B, L, v, d):
+    check(_lib.lib().mvlpt_set_prompt_rows(_p(x), _p(prompt), int(prompt.dtype == torch.float16), B, L, v, d, _stream()),
+          "mvlpt_set_prompt_rows")
+
+
+def prompt_grad(dx, dx16, grad, B, L, v, d, inv_scale, zero_rows):
+    check(_lib.lib().mvlpt_prompt_grad(_p(dx), _p(dx16), _p(grad), B, L, v, d, float(inv_scale), int(zero_rows),
+                                       _stream()), "mvlpt_prompt_grad")
+
+
+def text_assemble(emb, ctx, slot, pos, x0, C, Lt, n_ctx, d, csc):
+    f16 = int(ctx is not None and ctx.dtype == torch.float16)
+    check(_lib.lib().mvlpt_text_assemble(_p(emb), _p(ctx), f16, _p(slot), _p(pos), _p(x0), C, Lt, n_ctx, d, int(csc),
+                                         _stream()), "mvlpt_text_assemble")
+
+
+def ctx_grad(dx0, ctx_pos, grad, C, Lt, n_ctx, d, csc, inv_scale):
+    check(_lib.lib().mvlpt_ctx_grad(_p(dx0), _p(ctx_pos), _p(grad), C, Lt, n_ctx, d, int(csc), float(inv_scale),
+                                    _stream()), "mvlpt_ctx_grad")
+
+
+def l2norm_fwd(x, y16, y32, inv_norm, rows, e):
+    check(_lib.lib().mvlpt_l2norm_fwd(_p(x), _p(y16), _p(y32), _p(inv_norm), rows, e, _stream()), "mvlpt_l2norm_fwd")
+
+
+def l2norm_bwd(dy, y32, inv_norm, dx16, rows, e):
+    check(_lib.lib().mvlpt_l2norm_bwd(_p(dy), _p(y32), _p(inv_norm), _p(dx16), rows, e, _stream()), "mvlpt_l2norm_bwd")
+
+
+def ce_fwd_bwd(logits, ldc, label, soft, task, ranges, loss_rows, pred, dz16, B, C, coef):
+    check(_lib.lib().mvlpt_ce_fwd_bwd(_p(logits), ldc, _p(label), _p(soft), _p(task), _p(ranges), _p(loss_rows),
+                                      _p(pred), _p(dz16), B, C, float(coef), _stream()), "mvlpt_ce_fwd_bwd")
+
+
+def dlogits_prepare(dlogits, ld_in, task, ranges, dz16, ldc, B, C, coef):
+    check(_lib.lib().mvlpt_dlogits_prepare(_p(dlogits), ld_in, _p(task), _p(ranges), _p(dz16), ldc, B, C, float(coef),
+                                           _stream()), "mvlpt_dlogits_prepare")
+
+
+def task_mask(logits, ldc, task, ranges, B, C):
+    check(_lib.lib().mvlpt_task_mask(_p(logits), ldc, _p(task), _p(ranges), B, C, _stream()), "mvlpt_task_mask")
+
+
+def transpose_f16(inp, out, R, Cc, ld_in, ld_out):
+    check(_lib.lib().mvlpt_transpose_f16(_p(inp), _p(out), R, Cc, ld_in, ld_out, _stream()), "mvlpt_transpose_f16")
+
+
+def sgd(p, buf, g, lr, momentum, wd, first_step):
+    check(_lib.lib().mvlpt_sgd(_p(p), _p(buf), _p(g), p.numel(), int(p.dtype == torch.float16), float(lr),
+                               float(momentum), float(wd), int(first_step), _stream()), "mvlpt_sgd")
+
+
+def zero(t):
+    check(_lib.lib().mvlpt_zero(_p(t), t.numel() * t.element_size(), _stream()), "mvlpt_zero")

@@ -1,0 +1,519 @@
+"""B200-native mirror of the reference's trainers/mvlpt.py hot path.
+
+Same class names, constructor signatures, attribute names and state-dict keys as the reference
+(MultitaskVLPromptLearner :138-515, ImageEncoder :45-93, TextEncoder :95-130, CustomCLIP :517-583), so a Dassl
+config / checkpoint drops in unchanged — but no arithmetic happens in torch: forward and backward are sequenced
+by mvlpt_b200.engine over the sm_100a kernels of libmvlpt_sm100.so.  There is no CPU or eager fallback: calling a
+module with CPU tensors, or without the built library, raises.
+
+What is deliberately different (result-identical):
+  * prompts are never concatenated into activations — kernels read them from the prompt tables;
+  * 'middle'/'front' class-token positions use a precomputed index map instead of a Python loop over classes;
+  * text features are cached when no text-side parameter trains (VPT only);
+  * the EOT index is precomputed on the device (no per-call CPU argmax);
+  * activations keep an fp32 residual stream (the reference's is fp16), which only moves results closer to exact.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from functools import reduce
+from operator import mul
+from typing import Dict, List, Optional, Sequence
+
+import torch
+import torch.nn as nn
+
+from .. import engine as E
+from .. import ops
+from ..clip_model import FrozenCLIP, as_state_dict, build_model
+from ..tokenizer import EOT, SOT, get_tokenizer, tokenize
+from ..upt import UptProjection
+
+__all__ = ["load_clip_to_cpu", "ImageEncoder", "TextEncoder", "MultitaskVLPromptLearner", "CustomCLIP"]
+
+GRAD_SCALE = 4096.0  # power of two: exact; keeps fp16 dgrad operands in range (see engine.py)
+
+
+def load_clip_to_cpu(cfg, state_dict: Optional[Dict[str, torch.Tensor]] = None) -> FrozenCLIP:
+    """trainers/mvlpt.py:28-43.  The reference downloads a checkpoint by backbone name; offline the caller supplies
+    the state dict (or MODEL.BACKBONE.PATH points at a torch-saved one)."""
+    if state_dict is None:
+        path = getattr(cfg.MODEL.BACKBONE, "PATH", None)
+        if not path:
+            raise RuntimeError("no network: pass state_dict= or set cfg.MODEL.BACKBONE.PATH to a CLIP state dict")
+        obj = torch.load(path, map_location="cpu")
+        state_dict = obj.state_dict() if hasattr(obj, "state_dict") else obj
+    return build_model(state_dict)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# parameter containers that reproduce the reference's state-dict key names for the UPT projection
+# ---------------------------------------------------------------------------------------------------------------
+class _Linear(nn.Module):
+    def __init__(self, i: int, o: int, dtype):
+        super().__init__()
+        self.weight = nn.Parameter(torch.empty(o, i, dtype=dtype))
+        self.bias = nn.Parameter(torch.empty(o, dtype=dtype))
+        nn.init.kaiming_uniform_(self.weight, a=math.sqrt(5))
+        bound = 1 / math.sqrt(i)
+        nn.init.uniform_(self.bias, -bound, bound)
+
+
+class _LN(nn.Module):
+    def __init__(self, w: int):
+        super().__init__()
+        self.weight = nn.Parameter(torch.ones(w))
+        self.bias = nn.Parameter(torch.zeros(w))
+
+
+class _Attn(nn.Module):
+    def __init__(self, w: int):
+        super().__init__()
+        self.in_proj_weight = nn.Parameter(torch.empty(3 * w, w))
+        self.in_proj_bias = nn.Parameter(torch.zeros(3 * w))
+        self.out_proj = _Linear(w, w, torch.float32)
+        nn.init.xavier_uniform_(self.in_proj_weight)
+        nn.init.zeros_(self.out_proj.bias)
+
+
+class _ProjBlock(nn.Module):
+    """Parameters of the width-`w` ResidualAttentionBlock the reference uses as mvlpt_proj (fp32, :256-259)."""
+
+    def __init__(self, w: int):
+        super().__init__()
+        self.attn = _Attn(w)
+        self.ln_1 = _LN(w)
+        self.mlp = nn.ModuleDict(OrderedDict(c_fc=_Linear(w, 4 * w, torch.float32),
+                                             c_proj=_Linear(4 * w, w, torch.float32)))
+        self.ln_2 = _LN(w)
+
+
+class _ProjTransformer(nn.Module):
+    def __init__(self, w: int):
+        super().__init__()
+        self.width = w
+        self.resblocks = nn.ModuleList([_ProjBlock(w)])
+
+
+# ---------------------------------------------------------------------------------------------------------------
+class MultitaskVLPromptLearner(nn.Module):
+    """Owns every trainable tensor (trainers/mvlpt.py:139-325).  `tokenized_prompts` / `name_lens` may be supplied
+    when no BPE tokenizer is available (fixtures, synthetic benchmarks)."""
+
+    def __init__(self, cfg, classnames, clip_model, tokenized_prompts: Optional[torch.Tensor] = None,
+                 name_lens: Optional[Sequence[int]] = None):
+        super().__init__()
+        T = cfg.TRAINER.MVLPT
+        n_cls = len(classnames)
+        coop_n_ctx, cocoop_n_ctx, vpt_n_ctx = T.COOP.N_CTX, T.COCOOP.N_CTX, T.VPT.N_CTX
+        if cocoop_n_ctx != 0:
+            raise NotImplementedError("CoCoOp (trainers/mvlpt.py:260-290,348-374) is outside this build's hot path "
+                                      "(SURVEY.md §8f rank 3)")
+        dtype = clip_model.dtype
+        coop_ctx_dim = clip_model.ln_final.weight.shape[0]
+        vpt_ctx_dim = clip_model.visual.conv1.weight.shape[0]
+        patch = clip_model.visual.conv1.weight.shape[-1]
+        clip_imsize = clip_model.visual.input_resolution
+        cfg_imsize = cfg.INPUT.SIZE[0]
+        assert cfg_imsize == clip_imsize, f"cfg_imsize ({cfg_imsize}) must equal to clip_imsize ({clip_imsize})"
+
+        self.vpt_dropout = nn.Dropout(T.VPT.DROPOUT)
+        if T.VPT.DROPOUT != 0:
+            raise NotImplementedError("VPT.DROPOUT > 0 is not implemented (reference default 0.0, train.py:139)")
+        self.vpt_deep = T.VPT.DEEP
+        self.vpt_embeddings = None
+        self.vpt_embeddings_deep = None
+        prompt_prefix = None
+        if vpt_n_ctx != 0:
+            if T.VPT.PROJECT > -1:
+                raise NotImplementedError("VPT.PROJECT > -1 (vpt_proj Linear, trainers/mvlpt.py:170-175) not implemented")
+            self.vpt_proj = nn.Identity()
+            if T.VPT.CTX_INIT:
+                raise ValueError("CTX initiation scheme is not supported")
+            val = math.sqrt(6.0 / float(3 * reduce(mul, (patch, patch), 1) + vpt_ctx_dim))
+            self.vpt_embeddings = nn.Parameter(torch.zeros(1, vpt_n_ctx, vpt_ctx_dim, dtype=dtype))
+            nn.init.uniform_(self.vpt_embeddings.data, -val, val)
+            if self.vpt_deep:
+                self.vision_layers = len([k for k in clip_model.state_dict().keys()
+                                          if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])
+                self.vpt_embeddings_deep = nn.Parameter(
+                    torch.zeros(self.vision_layers - 1, vpt_n_ctx, vpt_ctx_dim, dtype=dtype))
+                nn.init.uniform_(self.vpt_embeddings_deep.data, -val, val)
+            prompt_prefix = "a photo of a "
+
+        self.ctx = None
+        if coop_n_ctx != 0:
+            if T.COOP.CTX_INIT:
+                init = T.COOP.CTX_INIT.replace("_", " ")
+                coop_n_ctx = len(init.split(" "))
+                with torch.no_grad():
+                    emb = clip_model.token_embedding(tokenize(init)).type(dtype)
+                ctx_vectors = emb[0, 1:1 + coop_n_ctx, :].clone()
+                prompt_prefix = init
+            else:
+                shape = (n_cls, coop_n_ctx, coop_ctx_dim) if T.COOP.CSC else (coop_n_ctx, coop_ctx_dim)
+                ctx_vectors = torch.empty(*shape, dtype=dtype)
+                nn.init.normal_(ctx_vectors, std=0.02)
+                prompt_prefix = " ".join(["X"] * coop_n_ctx)
+            self.ctx = nn.Parameter(ctx_vectors)
+
+        self.mvlpt_proj = nn.Identity()
+        if vpt_n_ctx != 0 and coop_n_ctx != 0:
+            self.mvlpt_proj_ctx_dim = T.PROJECT_DIM
+            method = T.PROJECT_METHOD
+            if method == "identity":
+                pass
+            elif method == "transformer":
+                pd = T.PROJECT_DIM
+                ident = lambda: nn.Identity()
+                self.mvlpt_proj_ctx_vpt_pre, self.mvlpt_proj_ctx_vpt_post = ident(), ident()
+                self.mvlpt_proj_ctx_coop_pre, self.mvlpt_proj_ctx_coop_post = ident(), ident()
+                if coop_ctx_dim != pd:
+                    self.mvlpt_proj_ctx_coop_pre = _Linear(coop_ctx_dim, pd, dtype)
+                    self.mvlpt_proj_ctx_coop_post = _Linear(pd, coop_ctx_dim, dtype)
+                if vpt_ctx_dim != pd:
+                    self.mvlpt_proj_ctx_vpt_pre = _Linear(vpt_ctx_dim, pd, dtype)
+                    self.mvlpt_proj_ctx_vpt_post = _Linear(pd, vpt_ctx_dim, dtype)
+                self.mvlpt_proj = _ProjTransformer(pd)
+            elif method == "mlp":
+                # the reference crashes here too (nn.GeLU does not exist, trainers/mvlpt.py:252-253)
+                raise AttributeError("module 'torch.nn' has no attribute 'GeLU'")
+            else:
+                raise ValueError(f"unknown PROJECT_METHOD {method!r}")
+        self.cocoop_ctx = None
+        self.meta_net = None
+
+        if prompt_prefix is None:
+            raise ValueError("at least one of VPT.N_CTX / COOP.N_CTX must be non-zero")
+        classnames = [name.replace("_", " ") for name in classnames]
+        if tokenized_prompts is None:
+            tok = get_tokenizer()
+            name_lens = [len(tok.encode(name)) for name in classnames]
+            prompts = [prompt_prefix + " " + name + "." for name in classnames]
+            if cfg.TRAINER.CUT_CONTEXTLEN:
+                max_length = min(clip_model.context_length, max(len(tok.encode(p)) + 2 for p in prompts))
+            else:
+                max_length = clip_model.context_length
+            tokenized_prompts = torch.cat([tokenize(p, context_length=max_length, tokenizer=tok) for p in prompts])
+        else:
+            if name_lens is None:
+                raise ValueError("name_lens must accompany tokenized_prompts")
+            tokenized_prompts = tokenized_prompts.clone().long()
+            if cfg.TRAINER.CUT_CONTEXTLEN:
+                used = int((tokenized_prompts != 0).sum(dim=1).max())
+                tokenized_prompts = tokenized_prompts[:, :min(clip_model.context_length, used)]
+        with torch.no_grad():
+            embedding = clip_model.token_embedding(tokenized_prompts).type(dtype)
+        # saved with the checkpoint, ignored on load (trainers/mvlpt.py:309-316, 1117-1121)
+        self.register_buffer("token_prefix", embedding[:, :1, :].clone())
+        self.register_buffer("token_suffix", embedding[:, 1 + coop_n_ctx:, :].clone())
+
+        self.n_cls = n_cls
+        self.vpt_n_ctx = vpt_n_ctx
+        self.coop_n_ctx = coop_n_ctx
+        self.cocoop_n_ctx = cocoop_n_ctx
+        self.tokenized_prompts = tokenized_prompts
+        self.name_lens = list(name_lens)
+        self.class_token_position = T.COOP.CLASS_TOKEN_POSITION
+        self.csc = bool(self.ctx is not None and self.ctx.dim() == 3)
+        # kernel-side view of the prompt layout (built once; replaces the per-class cat loop of :472-510)
+        Lt = tokenized_prompts.shape[1]
+        full = torch.cat([embedding[:, :1], torch.zeros(n_cls, coop_n_ctx, coop_ctx_dim, dtype=dtype),
+                          embedding[:, 1 + coop_n_ctx:]], dim=1).float()
+        pos = self.class_token_position if coop_n_ctx else "end"
+        self.register_buffer("_emb", E.rearrange_embedding(full, self.name_lens, coop_n_ctx, pos).contiguous(),
+                             persistent=False)
+        slot, ctx_pos = E.build_ctx_maps(self.name_lens, coop_n_ctx, Lt, pos)
+        self.register_buffer("_slot", slot, persistent=False)
+        self.register_buffer("_ctx_pos", ctx_pos, persistent=False)
+        eot = tokenized_prompts.argmax(dim=-1)
+        self.register_buffer("_eot_rows", (torch.arange(n_cls) * Lt + eot).to(torch.int32), persistent=False)
+        self._upt: Optional[UptProjection] = None
+
+    # ---- UPT -------------------------------------------------------------------------------------------------
+    @property
+    def uses_projection(self) -> bool:
+        return not (self.coop_n_ctx == 0 or isinstance(self.mvlpt_proj, nn.Identity) or self.vpt_n_ctx == 0)
+
+    def upt(self) -> UptProjection:
+        if self._upt is None:
+            self._upt = UptProjection(self)
+        return self._upt
+
+    def forward_mvlpt_proj(self, dtype=torch.float):
+        """trainers/mvlpt.py:376-414 -> (ctx', vpt', vpt_deep').  Identity pass-through unless both prompt kinds are on
+        and PROJECT_METHOD='transformer'."""
+        if not self.uses_projection:
+            return self.ctx, self.vpt_embeddings, self.vpt_embeddings_deep
+        return self.upt().forward()
+
+    # ---- assembly helpers kept for API parity (the fused kernels do this inside the towers) --------------------
+    def forward_vpt(self, x, vpt_embeddings=None):
+        """trainers/mvlpt.py:416-437.  The hot path never calls this (embed_assemble writes the rows directly)."""
+        if vpt_embeddings is None:
+            if self.vpt_embeddings is None:
+                return x
+            vpt_embeddings = self.vpt_embeddings
+        B = x.shape[0]
+        return torch.cat([x[:, :1, :], vpt_embeddings.expand(B, -1, -1).to(x.dtype), x[:, 1:, :]], dim=1)
+
+    def forward_coop(self, ctx=None):
+        """trainers/mvlpt.py:439-515: assembled prompt embeddings [n_cls, L_t, d_t] (without positional embedding)."""
+        if ctx is None:
+            ctx = self.ctx
+        if self.class_token_position not in ("end", "middle", "front"):
+            raise ValueError
+        C, Lt, d = self._emb.shape
+        _require_cuda(self._emb, "forward_coop")
+        out = torch.empty(C, Lt, d, device=self._emb.device, dtype=torch.float32)
+        zero_pos = torch.zeros(Lt, d, device=self._emb.device, dtype=torch.float32)
+        c = None if ctx is None else ctx.detach().contiguous()
+        ops.text_assemble(self._emb, c, self._slot, zero_pos, out, C, Lt, self.coop_n_ctx, d, self.csc)
+        return out.to(self._emb.dtype if ctx is None else ctx.dtype)
+
+    def forward_cocoop(self, im_features):
+        raise NotImplementedError("CoCoOp branch is outside this build's hot path (SURVEY.md §8f rank 3)")
+
+    def construct_prompts(self, ctx, prefix, suffix, label=None):
+        """trainers/mvlpt.py:327-346 (API parity)."""
+        if label is not None:
+            prefix, suffix = prefix[label], suffix[label]
+        return torch.cat([prefix, ctx, suffix], dim=1)
+
+
+def _require_cuda(t: torch.Tensor, who: str):
+    if not t.is_cuda:
+        raise ops._lib.MvlptError(f"{who}: tensors must live on a CUDA device (sm_100a); there is no CPU path")
+
+
+class ImageEncoder(nn.Module):
+    """trainers/mvlpt.py:45-93: forward(x, vpt_embeddings, vpt_embeddings_deep) -> [B, embed_dim] (forward only when
+    called directly; gradients flow through CustomCLIP)."""
+
+    def __init__(self, clip_model, mvlpt_model):
+        super().__init__()
+        self._sd = as_state_dict(clip_model)
+        self.__dict__["mvlpt_model"] = mvlpt_model  # not a submodule (avoid a registration cycle)
+        self._tower: Optional[E.ImageTower] = None
+        self._out_dtype = clip_model.dtype
+
+    def tower(self, device) -> E.ImageTower:
+        if self._tower is None:
+            self._tower = E.ImageTower(self._sd, device)
+        return self._tower
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor, vpt_embeddings=None, vpt_embeddings_deep=None):
+        _require_cuda(x, "ImageEncoder")
+        m = self.mvlpt_model
+        if vpt_embeddings is None:
+            vpt_embeddings = m.vpt_embeddings
+        deep = None
+        if m.vpt_deep and (vpt_embeddings_deep is not None or m.vpt_embeddings_deep is not None):
+            deep = vpt_embeddings_deep if vpt_embeddings_deep is not None else m.vpt_embeddings_deep
+        x = x.contiguous()
+        if x.dtype not in (torch.float16, torch.float32):
+            x = x.float()
+        cont = lambda t: None if t is None else t.detach().contiguous()
+        feat = self.tower(x.device).forward(x, cont(vpt_embeddings), cont(deep), train=False)
+        return feat.to(self._out_dtype)
+
+
+class TextEncoder(nn.Module):
+    """trainers/mvlpt.py:95-130: forward(prompts, tokenized_prompts) -> [n_cls, embed_dim] (forward only when called
+    directly).  CUT_CONTEXTLEN needs no mask surgery here (the causal mask is implicit) and ACT_CKPT has no B200
+    counterpart (everything fits in HBM)."""
+
+    def __init__(self, clip_model, cfg=None):
+        super().__init__()
+        self._sd = as_state_dict(clip_model)
+        self.dtype = clip_model.dtype
+        self.cfg = cfg
+        self._tower: Optional[E.TextTower] = None
+
+    def tower(self, device) -> E.TextTower:
+        if self._tower is None:
+            self._tower = E.TextTower(self._sd, device)
+        return self._tower
+
+    @torch.no_grad()
+    def forward(self, prompts: torch.Tensor, tokenized_prompts: torch.Tensor):
+        _require_cuda(prompts, "TextEncoder")
+        C, Lt, _ = prompts.shape
+        eot = tokenized_prompts.argmax(dim=-1).to(prompts.device)
+        rows = (torch.arange(C, device=prompts.device) * Lt + eot).to(torch.int32)
+        feat = self.tower(prompts.device).forward(prompts.float().contiguous(), None, None, rows, 0, False, train=False)
+        return feat.to(self.dtype)
+
+
+class _CustomCLIPFn(torch.autograd.Function):
+    """logits = f(image; prompt tensors): forward/backward are the hand-written engine passes."""
+
+    @staticmethod
+    def forward(ctx, model, image, task, train, *params):
+        logits = model._forward_core(image, task, train)
+        ctx.model, ctx.B, ctx.task, ctx.train = model, image.shape[0], task, train
+        ctx.n = len(params)
+        return logits[:, :model.prompt_learner.n_cls].to(model.dtype)
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        model = ctx.model
+        if not ctx.train:
+            raise RuntimeError("backward through a CustomCLIP forward that ran without gradient tracking")
+        grads = model._backward_core(ctx.B, dlogits=dlogits, task=ctx.task)
+        out = []
+        for name, p in model._trainables():
+            g = grads.get(name)
+            out.append(None if g is None else g.to(p.dtype).reshape(p.shape))
+        return (None, None, None, None, *out)
+
+
+class CustomCLIP(nn.Module):
+    """trainers/mvlpt.py:517-583."""
+
+    def __init__(self, cfg, classnames, clip_model, dm=None, tokenized_prompts=None, name_lens=None):
+        super().__init__()
+        self.prompt_learner = MultitaskVLPromptLearner(cfg, classnames, clip_model, tokenized_prompts, name_lens)
+        self.tokenized_prompts = self.prompt_learner.tokenized_prompts
+        self.image_encoder = ImageEncoder(clip_model, self.prompt_learner)
+        self.text_encoder = TextEncoder(clip_model, cfg)
+        self.logit_scale = clip_model.logit_scale
+        self.dtype = clip_model.dtype
+        self.grad_scale = GRAD_SCALE
+        self.cache_text_features = True
+        self._txt_cache_valid = False
+        self._head: Optional[E.LogitHead] = None
+        self._embed_dim = clip_model.visual.output_dim
+
+        self.multi_task_label_pertask = cfg.DATASET.MULTITASK_LABEL_PERTASK
+        self._task_ranges = None
+        if self.multi_task_label_pertask:
+            # per-task [start, end) class ranges, in task order (trainers/mvlpt.py:527-538)
+            rng, start = [], 0
+            for task in dm._task_names:
+                n = len(dm._labelmap[task])
+                rng.append((start, start + n))
+                start += n
+            self.class_index_pertask_start = torch.tensor([r[0] for r in rng])
+            self.class_index_pertask_end = torch.tensor([r[1] for r in rng])
+            self.register_buffer("_ranges", torch.tensor(rng, dtype=torch.int32), persistent=False)
+
+    # ---- plumbing ----------------------------------------------------------------------------------------------
+    def _trainables(self):
+        return [(n, p) for n, p in self.prompt_learner.named_parameters()]
+
+    def head(self, device) -> E.LogitHead:
+        if self._head is None:
+            self._head = E.LogitHead(float(self.logit_scale), self._embed_dim, device)
+        return self._head
+
+    def _task_dev(self, task, device):
+        if task is None or not self.multi_task_label_pertask:
+            return None, None
+        return task.to(device=device, dtype=torch.int32).contiguous(), self._ranges
+
+    # ---- engine passes -------------------------------------------------------------------------------------------
+    def _forward_core(self, image: torch.Tensor, task, train: bool) -> torch.Tensor:
+        """Runs projection -> image tower -> text tower -> logits (+ task mask); returns fp32 logits [B, ldc]."""
+        _require_cuda(image, "CustomCLIP")
+        pl = self.prompt_learner
+        dev = image.device
+        image = image.contiguous()
+        if image.dtype not in (torch.float16, torch.float32):
+            image = image.float()
+        B, C = image.shape[0], pl.n_cls
+        ctx, vpt, deep = pl.forward_mvlpt_proj(self.dtype)
+        if not pl.vpt_deep:
+            deep = None
+        cont = lambda t: None if t is None else t.detach().contiguous()
+        ctx, vpt, deep = cont(ctx), cont(vpt), cont(deep)
+        self._img_train = bool(train and vpt is not None)
+        self._txt_train = bool(train and ctx is not None)
+        self._shapes = dict(B=B, C=C, v=0 if vpt is None else vpt.shape[1],
+                            n_deep=None if deep is None else deep.shape[0], Lt=pl._emb.shape[1])
+        img_feat = self.image_encoder.tower(dev).forward(image, vpt, deep, train=self._img_train)
+        head = self.head(dev)
+        if ctx is not None or not (self.cache_text_features and self._txt_cache_valid == (B, C)):
+            txt_feat = self.text_encoder.tower(dev).forward(pl._emb, ctx, pl._slot, pl._eot_rows, pl.coop_n_ctx, pl.csc,
+                                                            train=self._txt_train)
+            head.normalize_text(txt_feat, B)
+            self._txt_cache_valid = (B, C) if ctx is None else False
+        logits = head.logits(img_feat, C)
+        t_dev, ranges = self._task_dev(task, dev)
+        if t_dev is not None:
+            ops.task_mask(logits, head.buffers(B, C)["ldc"], t_dev, ranges, B, C)
+        return logits
+
+    def _backward_core(self, B: int, dlogits: Optional[torch.Tensor] = None, task=None) -> Dict[str, torch.Tensor]:
+        """Head -> towers -> prompt gradients (fp32, unscaled).  With dlogits=None, dz16 was already produced by the fused
+        cross-entropy kernel."""
+        pl = self.prompt_learner
+        sh = self._shapes
+        C, v, n_deep, Lt = sh["C"], sh["v"], sh["n_deep"], sh["Lt"]
+        dev = pl._emb.device
+        head = self.head(dev)
+        bf = head.buffers(B, C)
+        if dlogits is not None:
+            t_dev, ranges = self._task_dev(task, dev)
+            dl = dlogits.float().contiguous()
+            ops.dlogits_prepare(dl, dl.stride(0), t_dev, ranges, bf["dz16"], bf["ldc"], B, C, self.grad_scale)
+        head.backward(B, C, need_img=self._img_train, need_txt=self._txt_train)
+        inv = 1.0 / self.grad_scale
+        grads: Dict[str, torch.Tensor] = {}
+        d_ctx = d_vpt = d_deep = None
+        if self._img_train:
+            it = self.image_encoder.tower(dev)
+            d_vpt = torch.empty(v, it.d, device=dev, dtype=torch.float32)
+            d_deep = torch.empty(n_deep, v, it.d, device=dev, dtype=torch.float32) if n_deep is not None else None
+            it.backward(bf["difeat16"], B, v, n_deep, d_vpt, d_deep, inv)
+        if self._txt_train:
+            tt = self.text_encoder.tower(dev)
+            shape = (C, pl.coop_n_ctx, tt.d) if pl.csc else (pl.coop_n_ctx, tt.d)
+            d_ctx = torch.empty(*shape, device=dev, dtype=torch.float32)
+            tt.backward(bf["dtfeat16"], C, Lt, pl._eot_rows, pl._ctx_pos, pl.coop_n_ctx, pl.csc, d_ctx, inv)
+        if pl.uses_projection:
+            grads.update(pl.upt().backward(d_ctx, d_vpt, d_deep))
+        else:
+            if d_ctx is not None:
+                grads["ctx"] = d_ctx
+            if d_vpt is not None:
+                grads["vpt_embeddings"] = d_vpt.unsqueeze(0)
+            if d_deep is not None:
+                grads["vpt_embeddings_deep"] = d_deep
+        return grads
+
+    # ---- public API ------------------------------------------------------------------------------------------------
+    def forward(self, image, task=None):
+        """trainers/mvlpt.py:540-583 -> logits [B, n_cls] (differentiable w.r.t. the prompt tensors)."""
+        params = [p for _, p in self._trainables()]
+        train = torch.is_grad_enabled() and any(p.requires_grad for p in params)
+        return _CustomCLIPFn.apply(self, image, task, train, *params)
+
+    def loss_and_grads(self, image, label, task=None, global_batch: Optional[int] = None):
+        """Fused train-step core (forward + cross-entropy + backward) without autograd: returns
+        (loss_rows fp32 [B], pred int32 [B], grads {name: fp32 tensor}).  `global_batch` is the divisor of the mean
+        (data-parallel ranks pass the global batch so that gradient all-reduce is a plain sum)."""
+        B = image.shape[0]
+        pl = self.prompt_learner
+        logits = self._forward_core(image, task, train=True)
+        dev = image.device
+        head = self.head(dev)
+        bf = head.buffers(B, pl.n_cls)
+        t_dev, ranges = self._task_dev(task, dev)
+        lab = soft = None
+        if label.dim() > 1 and label.shape[-1] > 1:
+            soft = label.to(device=dev, dtype=torch.float32).contiguous()
+        else:
+            lab = label.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
+        coef = self.grad_scale / float(global_batch or B)
+        ops.ce_fwd_bwd(logits, bf["ldc"], lab, soft, t_dev, ranges, bf["loss_rows"], bf["pred"], bf["dz16"], B, pl.n_cls,
+                       coef)
+        grads = self._backward_core(B)
+        return bf["loss_rows"], bf["pred"], grads
+
+    def last_logits(self, B: int) -> torch.Tensor:
+        """fp32 logits [B, n_cls] of the most recent pass (a view into the engine buffer)."""
+        C = self.prompt_learner.n_cls
+        return self.head(self.prompt_learner._emb.device).buffers(B, C)["logits"][:, :C]
