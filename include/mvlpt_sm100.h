@@ -128,7 +128,10 @@ int mvlpt_ctx_grad(const void* dx0, const void* ctx_pos, void* grad, int C, int 
  * mvlpt_ce_fwd_bwd: logits fp32 [B, ldc] (C valid columns) are first multiplied in place by the task mask
  *   (task int32 [B], ranges int32 [T,2]; NULL = no mask), then loss_rows[b] = CE(row, target) with integer
  *   labels (int64 [B]) or soft targets (fp32 [B,C], rows normalised to sum 1 inside); pred[b] = argmax;
+ *   hit[b] (int32, may be NULL) = pred[b] == label[b] (or == argmax of the soft row, trainers/mvlpt.py:935-936);
  *   dz16 fp16 [B, ldc] = coef * (softmax - y) * mask (may be NULL for evaluation).
+ * mvlpt_step_metrics: out2[0] = inv_div * sum(loss_rows) (batch-mean loss), out2[1] = 100 * mean(hit) (top-1
+ *   accuracy as dassl.metrics.compute_accuracy reports it, trainers/mvlpt.py:939-942); fp32 [2] on the device.
  * mvlpt_dlogits_prepare: dz16 = coef * dlogits * mask, for callers that compute their own loss (autograd).
  * mvlpt_transpose_f16: out[c,r] = in[r,c], zero padded to ld_out — operand layout for the head dgrads.
  * ------------------------------------------------------------------------------------------------ */
@@ -136,7 +139,9 @@ int mvlpt_l2norm_fwd(const void* x, void* y16, void* y32, void* inv_norm, int ro
 int mvlpt_l2norm_bwd(const void* dy, const void* y32, const void* inv_norm, void* dx16, int rows, int e,
                      mvlpt_stream_t stream);
 int mvlpt_ce_fwd_bwd(void* logits, int ldc, const void* label, const void* soft, const void* task, const void* ranges,
-                     void* loss_rows, void* pred, void* dz16, int B, int C, float coef, mvlpt_stream_t stream);
+                     void* loss_rows, void* pred, void* hit, void* dz16, int B, int C, float coef,
+                     mvlpt_stream_t stream);
+int mvlpt_step_metrics(const void* loss_rows, const void* hit, int B, float inv_div, void* out2, mvlpt_stream_t stream);
 int mvlpt_dlogits_prepare(const void* dlogits, int ld_in, const void* task, const void* ranges, void* dz16, int ldc,
                           int B, int C, float coef, mvlpt_stream_t stream);
 int mvlpt_transpose_f16(const void* in, void* out, int R, int Cc, int ld_in, int ld_out, mvlpt_stream_t stream);
@@ -148,6 +153,40 @@ int mvlpt_task_mask(void* logits, int ldc, const void* task, const void* ranges,
  * p/buf: fp16 (is_f16) or fp32; g: fp32 unscaled gradient. */
 int mvlpt_sgd(void* p, void* buf, const void* g, int n, int is_f16, float lr, float momentum, float wd, int first_step,
               mvlpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * UPT shared-prompt projection (MultitaskVLPromptLearner.forward_mvlpt_proj, trainers/mvlpt.py:376-414, modules
+ * :234-257, PROJECT_METHOD='transformer') — forward, and backward including the WEIGHT gradients of the projection
+ * modules (the only trainable weights of the step).  The reference's 1-layer "transformer" sees sequence length 1
+ * (SURVEY.md App. C): per token x += W_o(W_v LN1(x) + b_v) + b_o; x += W_pr quickgelu(W_fc LN2(x) + b_fc) + b_pr.
+ *   params / grads: arrays of MVLPT_UPT_NPARAM device pointers in the order of the enum below.  ctx, vpt, vpt_deep and
+ *   the four pre/post Linear tensors are fp16 when param_f16 (CLIP dtype) else fp32; the block's own tensors are always
+ *   fp32 (trainers/mvlpt.py:256-259).  Every gradient is fp32, same shape as its parameter.
+ *   ctx_out fp32 [n_ctx, dt]; vpt_out fp32 [(1+n_deep)*v, dv] (row block 0 = shallow prompts, then the deep ones).
+ *   workspace: mvlpt_upt_workspace(d) bytes; the forward leaves the activations the backward needs in it.
+ * ------------------------------------------------------------------------------------------------ */
+enum {
+    MVLPT_UPT_CTX = 0, MVLPT_UPT_VPT, MVLPT_UPT_VPT_DEEP,
+    MVLPT_UPT_COOP_PRE_W, MVLPT_UPT_COOP_PRE_B, MVLPT_UPT_COOP_POST_W, MVLPT_UPT_COOP_POST_B,
+    MVLPT_UPT_VPT_PRE_W, MVLPT_UPT_VPT_PRE_B, MVLPT_UPT_VPT_POST_W, MVLPT_UPT_VPT_POST_B,
+    MVLPT_UPT_LN1_G, MVLPT_UPT_LN1_B, MVLPT_UPT_IN_W, MVLPT_UPT_IN_B, MVLPT_UPT_OUT_W, MVLPT_UPT_OUT_B,
+    MVLPT_UPT_LN2_G, MVLPT_UPT_LN2_B, MVLPT_UPT_FC_W, MVLPT_UPT_FC_B, MVLPT_UPT_PROJ_W, MVLPT_UPT_PROJ_B,
+    MVLPT_UPT_NPARAM
+};
+typedef struct {
+    int n_ctx;     /* rows of ctx                                    */
+    int v;         /* visual prompts per layer                       */
+    int n_deep;    /* rows of vpt_embeddings_deep / v (0 = shallow)  */
+    int dt, dv;    /* text / vision widths                           */
+    int pd;        /* PROJECT_DIM                                    */
+    int param_f16; /* dtype of ctx / vpt / pre / post tensors        */
+} mvlpt_upt_desc;
+
+size_t mvlpt_upt_workspace(const mvlpt_upt_desc* d);
+int mvlpt_upt_fwd(const mvlpt_upt_desc* d, const void* const* params, void* workspace, size_t ws_bytes, void* ctx_out,
+                  void* vpt_out, mvlpt_stream_t stream);
+int mvlpt_upt_bwd(const mvlpt_upt_desc* d, const void* const* params, void* workspace, size_t ws_bytes,
+                  const void* d_ctx_out, const void* d_vpt_out, void* const* grads, mvlpt_stream_t stream);
 
 /* cudaMemsetAsync(p, 0, bytes) on the stream. */
 int mvlpt_zero(void* p, size_t bytes, mvlpt_stream_t stream);

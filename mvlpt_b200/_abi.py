@@ -7,7 +7,7 @@ from pathlib import Path
 
 HEADER = Path(__file__).resolve().parent.parent / "include" / "mvlpt_sm100.h"
 
-_PROTO = re.compile(r"^(int|uint64_t|const char\*)\s+(mvlpt_\w+)\s*\(([^;{]*)\)\s*;", re.M | re.S)
+_PROTO = re.compile(r"^(int|uint64_t|size_t|const char\*)\s+(mvlpt_\w+)\s*\(([^;{]*)\)\s*;", re.M | re.S)
 
 
 def _ctype(decl: str):
@@ -35,4 +35,5 @@ def declare(L) -> None:
     for name, (ret, args) in prototypes().items():
         fn = getattr(L, name)
         fn.argtypes = [_ctype(a) for a in args]
-        fn.restype = {"int": ctypes.c_int, "uint64_t": ctypes.c_uint64, "const char*": ctypes.c_char_p}[ret]
+        fn.restype = {"int": ctypes.c_int, "uint64_t": ctypes.c_uint64, "size_t": ctypes.c_size_t,
+                      "const char*": ctypes.c_char_p}[ret]

@@ -58,8 +58,8 @@ __global__ void l2norm_bwd_kernel(const float* __restrict__ dy, const float* __r
 // loss_i = -sum_c y_c log softmax(z)_c, dz = coef * (softmax(z) - y) * mask  (fp16, padded columns zeroed).
 __global__ void ce_kernel(float* __restrict__ logits, int ldc, const long long* __restrict__ label,
                           const float* __restrict__ soft, const int* __restrict__ task, const int* __restrict__ ranges,
-                          float* __restrict__ loss_rows, int* __restrict__ pred, __half* __restrict__ dz16, int C,
-                          float coef) {
+                          float* __restrict__ loss_rows, int* __restrict__ pred, int* __restrict__ hit,
+                          __half* __restrict__ dz16, int C, float coef) {
     __shared__ float red[32];
     __shared__ int redi[32];
     const int b = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
@@ -102,12 +102,34 @@ __global__ void ce_kernel(float* __restrict__ logits, int ldc, const long long* 
     am = redi[0];
     __syncthreads();
     float s = 0.f, ysum = 0.f;
+    float ym = -INFINITY;  // arg max of the soft target row = the "label" the reference scores accuracy against
+    int ya = 0x7fffffff;   // (trainers/mvlpt.py:935-936)
     for (int c = tid; c < C; c += blockDim.x) {
         s += __expf(z[c] - m);
-        if (soft) ysum += soft[(size_t)b * C + c];
+        if (soft) {
+            const float y = soft[(size_t)b * C + c];
+            ysum += y;
+            if (y > ym) { ym = y; ya = c; }
+        }
     }
     s = wsum(s);
     ysum = wsum(ysum);
+    if (soft && hit) {
+        for (int o = 16; o > 0; o >>= 1) {
+            const float om = __shfl_xor_sync(0xffffffffu, ym, o);
+            const int oa = __shfl_xor_sync(0xffffffffu, ya, o);
+            if (om > ym || (om == ym && oa < ya)) { ym = om; ya = oa; }
+        }
+        __syncthreads();
+        if (lane == 0) { red[warp] = ym; redi[warp] = ya; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int w = 1; w < nw; ++w)
+                if (red[w] > ym || (red[w] == ym && redi[w] < ya)) { ym = red[w]; ya = redi[w]; }
+            hit[b] = (ya == am);
+        }
+        __syncthreads();
+    }
     if (lane == 0) { red[warp] = s; }
     __syncthreads();
     float tot = 0.f;
@@ -143,6 +165,30 @@ __global__ void ce_kernel(float* __restrict__ logits, int ldc, const long long* 
         for (int w = 0; w < nw; ++w) t2 += red[w];
         loss_rows[b] = t2;
         pred[b] = am;
+        if (hit && !soft) hit[b] = (am == lab);
+    }
+}
+
+// out[0] = sum(loss_rows) * inv_div (the batch-mean loss, trainers/mvlpt.py:922/931), out[1] = 100 * mean(hit)
+// (dassl compute_accuracy top-1, trainers/mvlpt.py:941).  One block.
+__global__ void step_metrics_kernel(const float* __restrict__ loss_rows, const int* __restrict__ hit, int B, float inv_div,
+                                    float* __restrict__ out) {
+    __shared__ float red[2][32];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    float l = 0.f, h = 0.f;
+    for (int i = tid; i < B; i += blockDim.x) {
+        l += loss_rows[i];
+        h += hit ? (float)hit[i] : 0.f;
+    }
+    l = wsum(l);
+    h = wsum(h);
+    if (lane == 0) { red[0][warp] = l; red[1][warp] = h; }
+    __syncthreads();
+    if (tid == 0) {
+        float L = 0.f, H = 0.f;
+        for (int w = 0; w < nw; ++w) { L += red[0][w]; H += red[1][w]; }
+        out[0] = L * inv_div;
+        out[1] = 100.f * H / (float)B;
     }
 }
 
@@ -228,7 +274,8 @@ int mvlpt_l2norm_bwd(const void* dy, const void* y32, const void* inv_norm, void
 }
 
 int mvlpt_ce_fwd_bwd(void* logits, int ldc, const void* label, const void* soft, const void* task, const void* ranges,
-                     void* loss_rows, void* pred, void* dz16, int B, int C, float coef, mvlpt_stream_t stream) {
+                     void* loss_rows, void* pred, void* hit, void* dz16, int B, int C, float coef,
+                     mvlpt_stream_t stream) {
     if (!logits || !loss_rows || !pred || (!label && !soft)) return fail(MVLPT_EINVAL, "mvlpt_ce_fwd_bwd: null argument");
     if (B <= 0 || C <= 0 || ldc < C) return fail(MVLPT_EINVAL, "mvlpt_ce_fwd_bwd: bad sizes");
     int rc = require_sm100();
@@ -236,8 +283,18 @@ int mvlpt_ce_fwd_bwd(void* logits, int ldc, const void* label, const void* soft,
     ce_kernel<<<B, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<float*>(logits), ldc, static_cast<const long long*>(label), static_cast<const float*>(soft),
         static_cast<const int*>(task), static_cast<const int*>(ranges), static_cast<float*>(loss_rows),
-        static_cast<int*>(pred), static_cast<__half*>(dz16), C, coef);
+        static_cast<int*>(pred), static_cast<int*>(hit), static_cast<__half*>(dz16), C, coef);
     return launched("ce_fwd_bwd");
+}
+
+int mvlpt_step_metrics(const void* loss_rows, const void* hit, int B, float inv_div, void* out2, mvlpt_stream_t stream) {
+    if (!loss_rows || !out2) return fail(MVLPT_EINVAL, "mvlpt_step_metrics: null argument");
+    if (B <= 0) return fail(MVLPT_EINVAL, "mvlpt_step_metrics: B must be positive");
+    int rc = require_sm100();
+    if (rc) return rc;
+    step_metrics_kernel<<<1, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<const float*>(loss_rows), static_cast<const int*>(hit), B, inv_div, static_cast<float*>(out2));
+    return launched("step_metrics");
 }
 
 int mvlpt_dlogits_prepare(const void* dlogits, int ld_in, const void* task, const void* ranges, void* dz16, int ldc,

@@ -295,6 +295,7 @@ class LogitHead:
                 i16=z(B, e), i32=z(B, e, dt=F32), i_inv=z(B, dt=F32),
                 t16=z(C, e), t32=z(C, e, dt=F32), t_inv=z(C, dt=F32),
                 logits=z(B, ldc, dt=F32), dz16=z(B, ldc), loss_rows=z(B, dt=F32), pred=z(B, dt=I32),
+                hit=z(B, dt=I32), metrics=z(2, dt=F32),
                 t16_t=z(e, ldc), dz16_t=z(C, ldb), i16_t=z(e, ldb),
                 di32=z(B, e, dt=F32), dt32=z(C, e, dt=F32), difeat16=z(B, e), dtfeat16=z(C, e),
             )

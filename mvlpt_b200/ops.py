@@ -18,6 +18,39 @@ ACT_NONE, ACT_QUICKGELU, ACT_MUL_DQUICKGELU = 0, 1, 2
 LN_EPS = 1e-5
 
 
+class Profiler:
+    """Per-launch CUDA-event timing of the heavy kernels (bench.py's roofline pass).  While `ops.PROFILER` is set,
+    gemm / fmha / layer-norm wrappers bracket their launch with events on the current stream and record the
+    algorithmic FLOPs and bytes of that launch."""
+
+    def __init__(self):
+        self.records = []  # (kernel, start_event, end_event, flops, bytes)
+
+    def begin(self):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        return e
+
+    def end(self, kernel: str, start, flops: float, nbytes: float):
+        e = torch.cuda.Event(enable_timing=True)
+        e.record()
+        self.records.append((kernel, start, e, flops, nbytes))
+
+    def summary(self):
+        """{kernel: dict(launches, ms, flops, bytes)} — call after a device synchronize."""
+        out = {}
+        for k, a, b, f, n in self.records:
+            r = out.setdefault(k, dict(launches=0, ms=0.0, flops=0.0, bytes=0.0))
+            r["launches"] += 1
+            r["ms"] += a.elapsed_time(b)
+            r["flops"] += f
+            r["bytes"] += n
+        return out
+
+
+PROFILER: Optional[Profiler] = None
+
+
 def _p(t: Optional[torch.Tensor]):
     return None if t is None else ctypes.c_void_p(t.data_ptr())
 
@@ -49,28 +82,45 @@ def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid
     if not out_f32 and out.dtype != torch.float16:
         raise _lib.MvlptError("gemm out must be fp16 or fp32")
     d = GemmDesc(M, N, K, lda, ldw, ld_out, ld_aux, act, out_f32, float(alpha))
+    t0 = PROFILER.begin() if PROFILER is not None else None
     check(_lib.lib().mvlpt_gemm(byref(d), _p(A), _p(W), _p(bias), _p(aux_in), _p(aux_out), _p(resid), _p(out),
                                 _stream()), "mvlpt_gemm")
+    if t0 is not None:
+        nbytes = 2.0 * (M * K + N * K) + (4.0 if out_f32 else 2.0) * M * N + (4.0 * M * N if resid is not None else 0.0) \
+            + (2.0 * M * N if aux is not None else 0.0)
+        PROFILER.end("gemm_f16_tn", t0, 2.0 * M * N * K, nbytes)
     return out
 
 
 def fmha_fwd(qkv, out, lse, N, L, d, heads, causal):
+    t0 = PROFILER.begin() if PROFILER is not None else None
     check(_lib.lib().mvlpt_fmha_fwd(_p(qkv), _p(out), _p(lse), N, L, d, heads, int(causal), _stream()), "mvlpt_fmha_fwd")
+    if t0 is not None:  # algorithmic: full L^2 for causal too
+        PROFILER.end("fmha_fwd", t0, 4.0 * N * L * L * d, 2.0 * N * L * 4 * d + 4.0 * N * heads * L)
 
 
 def fmha_bwd(qkv, o, d_o, lse, dqkv, N, L, d, heads, causal):
+    t0 = PROFILER.begin() if PROFILER is not None else None
     check(_lib.lib().mvlpt_fmha_bwd(_p(qkv), _p(o), _p(d_o), _p(lse), _p(dqkv), N, L, d, heads, int(causal), _stream()),
           "mvlpt_fmha_bwd")
+    if t0 is not None:
+        PROFILER.end("fmha_bwd", t0, 8.0 * N * L * L * d, 2.0 * N * L * 8 * d + 4.0 * N * heads * L)
 
 
 def ln_fwd(x, gamma, beta, y, rows, d, row_index=None):
+    t0 = PROFILER.begin() if PROFILER is not None else None
     check(_lib.lib().mvlpt_ln_fwd(_p(x), _p(row_index), _p(gamma), _p(beta), _p(y), rows, d, LN_EPS, _stream()),
           "mvlpt_ln_fwd")
+    if t0 is not None:
+        PROFILER.end("ln_fwd", t0, 0.0, 6.0 * rows * d)
 
 
 def ln_bwd(dy, x, gamma, dx_stream, dx16, rows, d, accumulate, row_index=None):
+    t0 = PROFILER.begin() if PROFILER is not None else None
     check(_lib.lib().mvlpt_ln_bwd(_p(dy), _p(x), _p(row_index), _p(gamma), _p(dx_stream), _p(dx16), rows, d, LN_EPS,
                                   int(accumulate), _stream()), "mvlpt_ln_bwd")
+    if t0 is not None:
+        PROFILER.end("ln_bwd", t0, 0.0, (2.0 + 4.0 + 4.0 + (4.0 if accumulate else 0.0) + 2.0) * rows * d)
 
 
 def im2col(img, patches, B, H, W, p, Kp):
@@ -113,9 +163,14 @@ def l2norm_bwd(dy, y32, inv_norm, dx16, rows, e):
     check(_lib.lib().mvlpt_l2norm_bwd(_p(dy), _p(y32), _p(inv_norm), _p(dx16), rows, e, _stream()), "mvlpt_l2norm_bwd")
 
 
-def ce_fwd_bwd(logits, ldc, label, soft, task, ranges, loss_rows, pred, dz16, B, C, coef):
+def ce_fwd_bwd(logits, ldc, label, soft, task, ranges, loss_rows, pred, dz16, B, C, coef, hit=None):
     check(_lib.lib().mvlpt_ce_fwd_bwd(_p(logits), ldc, _p(label), _p(soft), _p(task), _p(ranges), _p(loss_rows),
-                                      _p(pred), _p(dz16), B, C, float(coef), _stream()), "mvlpt_ce_fwd_bwd")
+                                      _p(pred), _p(hit), _p(dz16), B, C, float(coef), _stream()), "mvlpt_ce_fwd_bwd")
+
+
+def step_metrics(loss_rows, hit, B, inv_div, out2):
+    check(_lib.lib().mvlpt_step_metrics(_p(loss_rows), _p(hit), B, float(inv_div), _p(out2), _stream()),
+          "mvlpt_step_metrics")
 
 
 def dlogits_prepare(dlogits, ld_in, task, ranges, dz16, ldc, B, C, coef):

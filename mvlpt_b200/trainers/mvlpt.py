@@ -30,7 +30,7 @@ from ..clip_model import FrozenCLIP, as_state_dict, build_model
 from ..tokenizer import EOT, SOT, get_tokenizer, tokenize
 from ..upt import UptProjection
 
-__all__ = ["load_clip_to_cpu", "ImageEncoder", "TextEncoder", "MultitaskVLPromptLearner", "CustomCLIP"]
+__all__ = ["load_clip_to_cpu", "ImageEncoder", "TextEncoder", "MultitaskVLPromptLearner", "CustomCLIP", "MVLPT"]
 
 GRAD_SCALE = 4096.0  # power of two: exact; keeps fp16 dgrad operands in range (see engine.py)
 
@@ -366,7 +366,8 @@ class _CustomCLIPFn(torch.autograd.Function):
         out = []
         for name, p in model._trainables():
             g = grads.get(name)
-            out.append(None if g is None else g.to(p.dtype).reshape(p.shape))
+            # the engine's gradients live in a reused flat buffer: hand autograd its own copy
+            out.append(None if g is None else g.reshape(p.shape).to(p.dtype, copy=True))
         return (None, None, None, None, *out)
 
 
@@ -446,9 +447,27 @@ class CustomCLIP(nn.Module):
             ops.task_mask(logits, head.buffers(B, C)["ldc"], t_dev, ranges, B, C)
         return logits
 
+    def grad_buffer(self) -> torch.Tensor:
+        """Flat fp32 gradient buffer over every trainable prompt tensor, in named_parameters() order.  The engine writes
+        prompt gradients straight into views of it, so data-parallel ranks all-reduce ONE tensor."""
+        dev = self.prompt_learner._emb.device
+        if getattr(self, "_grad_flat", None) is None or self._grad_flat.device != dev:
+            names = self._trainables()
+            total = sum(p.numel() for _, p in names)
+            self._grad_flat = torch.zeros(total, device=dev, dtype=torch.float32)
+            self._grad_views, off = {}, 0
+            for n, p in names:
+                self._grad_views[n] = self._grad_flat[off:off + p.numel()].view(p.shape)
+                off += p.numel()
+        return self._grad_flat
+
+    def grad_views(self) -> Dict[str, torch.Tensor]:
+        self.grad_buffer()
+        return self._grad_views
+
     def _backward_core(self, B: int, dlogits: Optional[torch.Tensor] = None, task=None) -> Dict[str, torch.Tensor]:
-        """Head -> towers -> prompt gradients (fp32, unscaled).  With dlogits=None, dz16 was already produced by the fused
-        cross-entropy kernel."""
+        """Head -> towers -> prompt gradients (fp32, unscaled), written into views of grad_buffer().  With dlogits=None,
+        dz16 was already produced by the fused cross-entropy kernel."""
         pl = self.prompt_learner
         sh = self._shapes
         C, v, n_deep, Lt = sh["C"], sh["v"], sh["n_deep"], sh["Lt"]
@@ -461,27 +480,34 @@ class CustomCLIP(nn.Module):
             ops.dlogits_prepare(dl, dl.stride(0), t_dev, ranges, bf["dz16"], bf["ldc"], B, C, self.grad_scale)
         head.backward(B, C, need_img=self._img_train, need_txt=self._txt_train)
         inv = 1.0 / self.grad_scale
+        views = self.grad_views()
+        proj = pl.uses_projection
         grads: Dict[str, torch.Tensor] = {}
         d_ctx = d_vpt = d_deep = None
         if self._img_train:
             it = self.image_encoder.tower(dev)
-            d_vpt = torch.empty(v, it.d, device=dev, dtype=torch.float32)
-            d_deep = torch.empty(n_deep, v, it.d, device=dev, dtype=torch.float32) if n_deep is not None else None
+            if proj:
+                _, d_vpt, d_deep = pl.upt().grad_input_views()
+            else:
+                d_vpt = views["vpt_embeddings"].view(v, it.d)
+                d_deep = views["vpt_embeddings_deep"] if n_deep is not None else None
             it.backward(bf["difeat16"], B, v, n_deep, d_vpt, d_deep, inv)
         if self._txt_train:
             tt = self.text_encoder.tower(dev)
-            shape = (C, pl.coop_n_ctx, tt.d) if pl.csc else (pl.coop_n_ctx, tt.d)
-            d_ctx = torch.empty(*shape, device=dev, dtype=torch.float32)
+            if proj:
+                d_ctx = pl.upt().grad_input_views()[0]
+            else:
+                d_ctx = views["ctx"]
             tt.backward(bf["dtfeat16"], C, Lt, pl._eot_rows, pl._ctx_pos, pl.coop_n_ctx, pl.csc, d_ctx, inv)
-        if pl.uses_projection:
-            grads.update(pl.upt().backward(d_ctx, d_vpt, d_deep))
+        if proj:
+            pl.upt().backward(views)
+            grads = dict(views)
         else:
-            if d_ctx is not None:
-                grads["ctx"] = d_ctx
-            if d_vpt is not None:
-                grads["vpt_embeddings"] = d_vpt.unsqueeze(0)
-            if d_deep is not None:
-                grads["vpt_embeddings_deep"] = d_deep
+            for k in ("ctx", "vpt_embeddings", "vpt_embeddings_deep"):
+                if k in views:
+                    grads[k] = views[k]
+            if d_deep is None and "vpt_embeddings_deep" in grads:
+                ops.zero(grads["vpt_embeddings_deep"])
         return grads
 
     # ---- public API ------------------------------------------------------------------------------------------------
@@ -509,11 +535,222 @@ class CustomCLIP(nn.Module):
             lab = label.reshape(-1).to(device=dev, dtype=torch.int64).contiguous()
         coef = self.grad_scale / float(global_batch or B)
         ops.ce_fwd_bwd(logits, bf["ldc"], lab, soft, t_dev, ranges, bf["loss_rows"], bf["pred"], bf["dz16"], B, pl.n_cls,
-                       coef)
+                       coef, hit=bf["hit"])
+        ops.step_metrics(bf["loss_rows"], bf["hit"], B, 1.0 / B, bf["metrics"])
         grads = self._backward_core(B)
         return bf["loss_rows"], bf["pred"], grads
+
+    def last_metrics(self, B: int) -> torch.Tensor:
+        """Device fp32 [2] = (batch-mean loss, top-1 accuracy %) of the most recent loss_and_grads call."""
+        return self.head(self.prompt_learner._emb.device).buffers(B, self.prompt_learner.n_cls)["metrics"]
 
     def last_logits(self, B: int) -> torch.Tensor:
         """fp32 logits [B, n_cls] of the most recent pass (a view into the engine buffer)."""
         C = self.prompt_learner.n_cls
         return self.head(self.prompt_learner._emb.device).buffers(B, C)["logits"][:, :C]
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Trainer (trainers/mvlpt.py:827-1125).  The reference subclasses Dassl's TrainerX; Dassl is not installable here,
+# so the handful of inherited members it uses (SURVEY.md App. F) are provided by this class itself.
+# ---------------------------------------------------------------------------------------------------------------
+class MVLPT:
+    """Drop-in for the reference's `MVLPT(TrainerX)`: same cfg keys, same method names, same batch formats, same
+    `forward_backward -> {"loss", "acc"[, "num_tasks"]}` contract.  One process per GPU; with torch.distributed
+    initialised the prompt gradients are SUM-all-reduced over NCCL (replaces nn.DataParallel, :877-880)."""
+
+    def __init__(self, cfg, dm=None, clip_state_dict=None, device=None, tokenized_prompts=None, name_lens=None,
+                 dp=None):
+        from . import runtime as R
+        self.check_cfg(cfg)
+        self.cfg = cfg
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if device is None:
+            raise ops._lib.MvlptError("MVLPT trainer needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device(device)
+        self.dp = dp if dp is not None else R.DataParallelGroup()
+        self._models, self._optims, self._scheds = OrderedDict(), OrderedDict(), OrderedDict()
+        self.epoch, self.start_epoch = 0, 0
+        self.max_epoch = cfg.OPTIM.MAX_EPOCH
+        self.batch_idx, self.num_batches = 0, 1
+        self._clip_state_dict = clip_state_dict
+        self._tok = (tokenized_prompts, name_lens)
+        self.dm = dm
+        self.build_data_loader()
+        self.build_model()
+
+    # ---- reference API -------------------------------------------------------------------------------------------
+    def check_cfg(self, cfg):
+        assert cfg.TRAINER.MVLPT.PREC in ["fp16", "fp32", "amp"]
+
+    def build_data_loader(self):
+        """trainers/mvlpt.py:883-908.  The reference builds one of three Dassl/ELEVATER data managers from files on
+        disk (out of scope, SURVEY.md §2 #8); here the caller passes any object exposing the same attributes."""
+        dm = self.dm
+        self.multi_task = self.cfg.DATASET.MULTITASK
+        self.multi_task_label_pertask = self.cfg.DATASET.MULTITASK_LABEL_PERTASK
+        if dm is None:
+            raise ValueError("pass dm= (an object with the DataManager attributes: dataset.classnames | lab2cname, "
+                             "num_classes, train_loader_x, val_loader, test_loader)")
+        self.train_loader_x = getattr(dm, "train_loader_x", None)
+        self.train_loader_u = getattr(dm, "train_loader_u", None)
+        self.val_loader = getattr(dm, "val_loader", None)
+        self.test_loader = getattr(dm, "test_loader", None)
+        self.num_classes = dm.num_classes
+        self.num_source_domains = getattr(dm, "num_source_domains", 1)
+        self.lab2cname = dm.lab2cname
+        if self.train_loader_x is not None and hasattr(self.train_loader_x, "__len__"):
+            self.num_batches = len(self.train_loader_x)
+
+    def build_model(self):
+        """trainers/mvlpt.py:838-880."""
+        from . import runtime as R
+        cfg = self.cfg
+        classnames = self.dm.dataset.classnames if cfg.DATASET.COOP else list(self.dm.lab2cname.values())
+        clip_model = load_clip_to_cpu(cfg, self._clip_state_dict)
+        if cfg.TRAINER.MVLPT.PREC in ("fp32", "amp"):
+            clip_model.float()
+        self.model = CustomCLIP(cfg, classnames, clip_model, dm=self.dm, tokenized_prompts=self._tok[0],
+                                name_lens=self._tok[1])
+        # only prompt_learner.* is trainable; the CLIP towers are frozen kernel inputs, not nn.Parameters (:856-858)
+        for name, param in self.model.named_parameters():
+            param.requires_grad_("prompt_learner" in name)
+        if getattr(cfg.MODEL, "INIT_WEIGHTS", ""):
+            sd = torch.load(cfg.MODEL.INIT_WEIGHTS, map_location="cpu")
+            self.model.prompt_learner.load_state_dict(sd.get("state_dict", sd), strict=False)
+        self.model.to(self.device)
+        self.optim = R.build_optimizer(self.model._trainables(), cfg.OPTIM)
+        self.sched = R.build_lr_scheduler(self.optim, cfg.OPTIM)
+        self.register_model("prompt_learner", self.model.prompt_learner, self.optim, self.sched)
+        self.scaler = None  # amp: the kernels already scale gradients by a fixed power of two (engine.py)
+        self._metrics_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+
+    def forward_backward(self, batch):
+        """trainers/mvlpt.py:910-951: forward, cross-entropy, backward, SGD step; returns the loss summary."""
+        image, label, tasks_ = self.parse_batch_train(batch)
+        B = image.shape[0]
+        model = self.model
+        # soft (multi-hot) labels are row-normalised inside the cross-entropy kernel (:914-916)
+        model.loss_and_grads(image, label, tasks_, global_batch=B * self.dp.world)
+        flat = model.grad_buffer()
+        self.dp.all_reduce_sum(flat)
+        self.optim.step(flat)
+        self._metrics_host.copy_(model.last_metrics(B), non_blocking=True)
+        torch.cuda.current_stream().synchronize()  # the reference's two .item() calls (:939-942)
+        loss_summary = {"loss": float(self._metrics_host[0]), "acc": float(self._metrics_host[1])}
+        if tasks_ is not None:
+            loss_summary.update({"num_tasks": len(set(tasks_.tolist()))})
+        if (self.batch_idx + 1) == self.num_batches:
+            self.update_lr()
+        return loss_summary
+
+    def _parse(self, batch):
+        if self.cfg.DATASET.COOP:
+            inp_key, lab_key, task_key = "img", "label", "domain"
+        else:
+            inp_key, lab_key, task_key = 0, 1, 3
+        input, label = batch[inp_key], batch[lab_key]
+        tasks = batch[task_key] if self.multi_task else None
+        input = input.to(self.device, non_blocking=True)
+        label = label.to(self.device, non_blocking=True)
+        return input, label, tasks
+
+    def parse_batch_train(self, batch):
+        return self._parse(batch)
+
+    def parse_batch_test(self, batch):
+        return self._parse(batch)
+
+    @torch.no_grad()
+    def model_inference(self, input, task=None):
+        return self.model(input, task=task)
+
+    @torch.no_grad()
+    def test(self, split=None):
+        """trainers/mvlpt.py:989-1088, reduced to its arithmetic: top-1 accuracy of model_inference over a loader
+        (per task when multi_task).  The ELEVATER metric zoo (mean-per-class, 11-pt mAP) is out of scope."""
+        self.set_model_mode("eval")
+        split = split or self.cfg.TEST.SPLIT
+        loader = self.val_loader if split == "val" and self.val_loader is not None else self.test_loader
+        correct, total = {}, {}
+        for batch in loader:
+            image, label, tasks_ = self.parse_batch_test(batch)
+            out = self.model_inference(image, task=tasks_)
+            if label.dim() > 1 and label.shape[-1] > 1:
+                label = label.argmax(dim=1)
+            hit = (out.argmax(dim=1) == label).cpu()
+            keys = tasks_.tolist() if tasks_ is not None else [0] * len(hit)
+            for k, h in zip(keys, hit.tolist()):
+                correct[k] = correct.get(k, 0) + int(h)
+                total[k] = total.get(k, 0) + 1
+        per_task = {k: 100.0 * correct[k] / total[k] for k in total}
+        results = {"accuracy": sum(per_task.values()) / max(1, len(per_task))}
+        results.update({f"task{k}/accuracy": v for k, v in per_task.items()})
+        return results
+
+    def load_model(self, directory, epoch=None):
+        """trainers/mvlpt.py:1090-1125: <dir>/prompt_learner/model-best.pth.tar | model.pth.tar-<epoch>; renames
+        upt_proj -> mvlpt_proj, drops token_prefix/token_suffix, loads non-strictly."""
+        import os.path as osp
+        if not directory:
+            print("Note that load_model() is skipped as no pretrained model is given")
+            return
+        model_file = "model-best.pth.tar" if epoch is None else "model.pth.tar-" + str(epoch)
+        for name in self.get_model_names():
+            model_path = osp.join(directory, name, model_file)
+            if not osp.exists(model_path):
+                raise FileNotFoundError('Model not found at "{}"'.format(model_path))
+            checkpoint = torch.load(model_path, map_location="cpu", weights_only=False)
+            state_dict = {k.replace("upt_proj", "mvlpt_proj"): v for k, v in checkpoint["state_dict"].items()}
+            for k in ("token_prefix", "token_suffix"):
+                state_dict.pop(k, None)
+            print('Loading weights to {} from "{}" (epoch = {})'.format(name, model_path, checkpoint.get("epoch")))
+            self._models[name].load_state_dict(state_dict, strict=False)
+            self.model._txt_cache_valid = False
+
+    # ---- members the reference inherits from Dassl's TrainerX (SURVEY.md App. F) ------------------------------------
+    def register_model(self, name="model", model=None, optim=None, sched=None):
+        self._models[name], self._optims[name], self._scheds[name] = model, optim, sched
+
+    def get_model_names(self, names=None):
+        return list(self._models.keys()) if names is None else list(names)
+
+    def set_model_mode(self, mode="train", names=None):
+        for name in self.get_model_names(names):
+            self._models[name].train(mode == "train")
+
+    def update_lr(self, names=None):
+        for name in self.get_model_names(names):
+            if self._scheds[name] is not None:
+                self._scheds[name].step()
+
+    def get_current_lr(self, names=None):
+        return self._optims[self.get_model_names(names)[0]].param_groups[0]["lr"]
+
+    def save_model(self, epoch, directory, is_best=False, val_result=None, model_name=""):
+        """Dassl's checkpoint layout (SURVEY.md §3.4): <dir>/<name>/model.pth.tar-<epoch> (+ model-best.pth.tar)."""
+        import os
+        import os.path as osp
+        for name in self.get_model_names():
+            ckpt = {"state_dict": {k: v.detach().cpu() for k, v in self._models[name].state_dict().items()},
+                    "epoch": epoch, "optimizer": self._optims[name].state_dict(), "val_result": val_result}
+            os.makedirs(osp.join(directory, name), exist_ok=True)
+            fpath = osp.join(directory, name, model_name or f"model.pth.tar-{epoch}")
+            torch.save(ckpt, fpath)
+            if is_best:
+                torch.save(ckpt, osp.join(directory, name, "model-best.pth.tar"))
+
+    def run_epoch(self):
+        self.set_model_mode("train")
+        self.num_batches = len(self.train_loader_x)
+        last = None
+        for self.batch_idx, batch in enumerate(self.train_loader_x):
+            last = self.forward_backward(batch)
+        return last
+
+    def train(self):
+        last = None
+        for self.epoch in range(self.start_epoch, self.max_epoch):
+            last = self.run_epoch()
+        return last

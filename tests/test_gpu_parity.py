@@ -1,0 +1,140 @@
+"""GPU parity: the CUDA path (through the C ABI, via the reference-API mirror) against the CPU oracle on the same
+seeded inputs and against the golden fixtures generated from the reference itself (oracle/gen_golden.py).
+
+Tolerances: the reference's OWN fp16 path sits 2.7e-3 (logits) / 2e-2 (gradients) away from exact
+arithmetic; BASELINE.json asks 1e-3 fp16-relative.  Our kernels keep fp32 accumulators and an fp32 residual stream;
+what remains is the fp16 rounding of GEMM operands.  Bars, normwise-max relative error against the fp32 reference:
+  logits  <= 3e-3 (tiny random-init models: features ~N(0,1) make this the noise floor of fp16 operands)
+  grads   <= 2e-2 and argmax bit-exact on every sample whose fp32 top-2 margin exceeds 4 fp16 ulps.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 3e-3
+GRAD_TOL = 2e-2
+
+TINY = ["tiny_coop_end", "tiny_coop_middle_cut", "tiny_coop_front_csc", "tiny_vpt_shallow", "tiny_vpt_deep",
+        "tiny_vpt_deep_taskmask_soft", "tiny_upt_identity", "tiny_upt_transformer"]
+FULL = ["b16_coop_end", "b16_vpt_deep", "b16_upt_transformer", "b32_coop_cfg1", "l14_coop_end"]
+
+
+def _run(name, prec):
+    from tests.helpers import build_custom_clip, rel_err
+    model, fx, case, sd, image, pp, upt = build_custom_clip(name, prec)
+    img = image.cuda()
+    if prec == "fp16":
+        img = img.half()
+    loss_rows, pred, grads = model.loss_and_grads(img, fx["label"].cuda(), fx["task"])
+    torch.cuda.synchronize()
+    logits = model.last_logits(img.shape[0]).float().cpu()
+    return model, fx, case, sd, image, pp, upt, logits, loss_rows.cpu(), pred.cpu(), {k: g.cpu() for k, g in grads.items()}
+
+
+def _check_against(fx_logits, fx_loss, fx_grads, margin, logits, loss_rows, pred, grads):
+    from tests.helpers import rel_err
+    assert rel_err(logits, fx_logits) <= LOGIT_TOL
+    assert abs(float(loss_rows.mean()) - float(fx_loss)) <= 5e-3 * max(1.0, abs(float(fx_loss)))
+    ulp = 9.8e-4 * fx_logits.abs().max()
+    safe = margin > 4 * ulp
+    assert torch.equal(logits.argmax(-1)[safe], fx_logits.argmax(-1)[safe])
+    assert torch.equal(pred.long()[safe], fx_logits.argmax(-1)[safe])
+    for k, g in fx_grads.items():
+        assert k in grads, f"missing gradient {k}"
+        assert rel_err(grads[k].reshape(g.shape), g) <= GRAD_TOL, k
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", TINY + FULL)
+def test_step_matches_reference_golden(name, prec):
+    """logits, loss, argmax and every prompt gradient vs the fixture produced by the reference's own CustomCLIP."""
+    model, fx, case, sd, image, pp, upt, logits, loss_rows, pred, grads = _run(name, prec)
+    _check_against(fx["logits"], fx["loss"], fx["grads"], fx["top2_margin"], logits, loss_rows, pred, grads)
+
+
+@pytest.mark.parametrize("name", TINY)
+def test_step_matches_oracle_on_fresh_inputs(name):
+    """Same comparison against the oracle run live on differently seeded images/labels (not the fixture's)."""
+    from oracle import mvlpt_oracle as O
+    from mvlpt_b200 import synth
+    from tests.helpers import build_custom_clip, oracle_kwargs
+    model, fx, case, sd, image, pp, upt = build_custom_clip(name, "fp32")
+    B = 5
+    image = synth.synth_images(B, synth.ARCHS[case["arch"]]["image_resolution"], seed=77)
+    g = torch.Generator().manual_seed(123)
+    kw = oracle_kwargs(fx, case, sd, upt)
+    task = None
+    if fx["task"] is not None:
+        task = torch.randint(0, len(case["tasks"]), (B,), generator=g)
+        kw["task"] = task
+    if fx["label"].dim() > 1:
+        label = torch.zeros(B, case["C"])
+        label[torch.arange(B), torch.randint(0, case["C"], (B,), generator=g)] = 1.0
+        label[torch.arange(B), torch.randint(0, case["C"], (B,), generator=g)] = 1.0
+    else:
+        label = torch.randint(0, case["C"], (B,), generator=g)
+    o_logits, o_loss, o_grads = O.train_step(image, label, sd, pp, **kw)
+    loss_rows, pred, grads = model.loss_and_grads(image.cuda(), label.cuda(), task)
+    torch.cuda.synchronize()
+    logits = model.last_logits(B).float().cpu()
+    top2 = o_logits.topk(2, dim=-1).values
+    _check_against(o_logits, o_loss, o_grads, top2[:, 0] - top2[:, 1], logits, loss_rows.cpu(), pred.cpu(),
+                   {k: v.cpu() for k, v in grads.items()})
+
+
+@pytest.mark.parametrize("name", ["tiny_coop_end", "tiny_vpt_deep", "tiny_upt_identity"])
+def test_autograd_path_equals_fused_path(name):
+    """CustomCLIP.forward + F.cross_entropy + .backward() (how the reference trainer drives it) gives the same
+    gradients as the fused loss_and_grads call."""
+    import torch.nn.functional as F
+    from tests.helpers import build_custom_clip, rel_err
+    model, fx, case, sd, image, pp, upt = build_custom_clip(name, "fp32")
+    img, lab = image.cuda(), fx["label"].cuda()
+    _, _, grads = model.loss_and_grads(img, lab, fx["task"])
+    fused = {k: v.clone() for k, v in grads.items()}
+    out = model(img, task=fx["task"])
+    F.cross_entropy(out.float(), lab).backward()
+    for k, p in model.prompt_learner.named_parameters():
+        if k in fused:
+            assert rel_err(p.grad.float().reshape(fused[k].shape), fused[k]) < 2e-3, k
+
+
+def test_encoders_match_golden_features():
+    """ImageEncoder / TextEncoder called directly (reference signatures) reproduce the reference features."""
+    from tests.helpers import build_custom_clip, rel_err
+    model, fx, case, sd, image, pp, upt = build_custom_clip("tiny_vpt_deep", "fp32")
+    f = model.image_encoder(image.cuda())
+    assert rel_err(f.float().cpu(), fx["image_features"]) < 3e-3
+    model, fx, case, sd, image, pp, upt = build_custom_clip("tiny_coop_middle_cut", "fp32")
+    prompts = model.prompt_learner.forward_coop()
+    assert rel_err(prompts.float().cpu(), fx["prompts"]) < 1e-3
+    t = model.text_encoder(prompts, model.tokenized_prompts)
+    assert rel_err(t.float().cpu(), fx["text_features"]) < 3e-3
+
+
+def test_full_size_properties():
+    """BASELINE-size batch (ViT-B/16, B=64 here to bound test time): size-independent properties —
+    (1) batch independence: logits of image i do not depend on the other images in the batch;
+    (2) gradient linearity: the prompt gradient of a batch equals the weighted sum over two half batches;
+    (3) the frozen CLIP weights are bit-identical before and after a step."""
+    from mvlpt_b200 import synth
+    from tests.helpers import build_custom_clip, rel_err
+    model, fx, case, sd, image, pp, upt = build_custom_clip("b16_vpt_deep", "fp16")
+    B, C = 64, case["C"]
+    img = synth.synth_images(B, 224, seed=5).half().cuda()
+    lab = torch.randint(0, C, (B,), generator=torch.Generator().manual_seed(1)).cuda()
+    tower = model.image_encoder.tower(img.device)
+    w_before = [b.w_qkv.clone() for b in tower.blocks[:2]]
+    _, _, g_full = model.loss_and_grads(img, lab)
+    g_full = {k: v.clone() for k, v in g_full.items()}
+    logits_full = model.last_logits(B).clone()
+    _, _, g_a = model.loss_and_grads(img[:32], lab[:32], global_batch=B)
+    g_a = {k: v.clone() for k, v in g_a.items()}
+    logits_a = model.last_logits(32).clone()
+    _, _, g_b = model.loss_and_grads(img[32:], lab[32:], global_batch=B)
+    assert torch.equal(logits_full[:32], logits_a)
+    for k in g_full:
+        assert rel_err(g_a[k] + g_b[k], g_full[k]) < 2e-3, k
+    for b, w in zip(tower.blocks[:2], w_before):
+        assert torch.equal(b.w_qkv, w)

@@ -1,0 +1,81 @@
+"""The MVLPT trainer mirror on the GPU: forward_backward contract, SGD trajectory vs the CPU oracle, checkpoints."""
+from types import SimpleNamespace as NS
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _trainer(name, prec="fp32", lr=0.002):
+    from mvlpt_b200.trainers.mvlpt import MVLPT
+    from mvlpt_b200.trainers.runtime import default_cfg
+    from tests.helpers import case_inputs
+    fx, case, arch, sd, image, pp, upt = case_inputs(name)
+    cfg = default_cfg()
+    T = cfg.TRAINER.MVLPT
+    T.PREC = prec
+    T.PROJECT_METHOD = case.get("project_method", "identity")
+    T.PROJECT_DIM = case.get("project_dim", 128)
+    T.VPT.N_CTX, T.VPT.DEEP = case.get("vpt_n_ctx", 0), case.get("vpt_deep", False)
+    T.COOP.N_CTX, T.COOP.CSC = case.get("coop_n_ctx", 0), case.get("csc", False)
+    T.COOP.CLASS_TOKEN_POSITION = case.get("position", "end")
+    cfg.TRAINER.CUT_CONTEXTLEN = case.get("cut", False)
+    cfg.INPUT.SIZE = (arch["image_resolution"],) * 2
+    cfg.DATASET.COOP = True
+    cfg.OPTIM.LR = lr
+    cfg.OPTIM.WARMUP_EPOCH = 0
+    dm = NS(dataset=NS(classnames=fx["names"]), lab2cname=dict(enumerate(fx["names"])), num_classes=case["C"])
+    tr = MVLPT(cfg, dm=dm, clip_state_dict=sd, tokenized_prompts=fx["tokenized_prompts"], name_lens=fx["name_lens"])
+    tr.model.prompt_learner.load_state_dict(pp, strict=False)
+    return tr, fx, case, sd, image, pp, upt
+
+
+@pytest.mark.parametrize("name", ["tiny_coop_end", "tiny_vpt_deep", "tiny_upt_identity"])
+def test_three_sgd_steps_follow_the_oracle(name):
+    from oracle import mvlpt_oracle as O
+    from tests.helpers import oracle_kwargs, rel_err
+    tr, fx, case, sd, image, pp, upt = _trainer(name, "fp32", lr=0.5)  # large lr so the trajectory is visible
+    tr.num_batches = 100
+    keys = list(pp)
+    params = [pp[k].clone() for k in keys]
+    bufs = [None] * len(keys)
+    kw = oracle_kwargs(fx, case, sd, upt)
+    batch = {"img": image, "label": fx["label"], "domain": torch.zeros(len(fx["label"]), dtype=torch.long)}
+    for step in range(3):
+        o_logits, o_loss, o_grads = O.train_step(image, fx["label"], sd, dict(zip(keys, params)), **kw)
+        bufs = O.sgd_step(params, [o_grads[k] for k in keys], bufs, lr=0.5)
+        s = tr.forward_backward(batch)
+        assert set(s) == {"loss", "acc"}
+        assert abs(s["loss"] - float(o_loss)) < 5e-3 * max(1.0, float(o_loss))
+        acc = 100.0 * float((o_logits.argmax(-1) == fx["label"]).float().mean())
+        assert abs(s["acc"] - acc) < 1e-3
+    mine = dict(tr.model.prompt_learner.named_parameters())
+    for k, p in zip(keys, params):
+        assert rel_err(mine[k].detach().float().cpu().reshape(p.shape), p) < 5e-3, k
+
+
+def test_checkpoint_roundtrip_and_reference_key_names(tmp_path):
+    tr, fx, case, sd, image, pp, upt = _trainer("tiny_upt_identity")
+    sdict = tr.model.prompt_learner.state_dict()
+    assert {"ctx", "vpt_embeddings", "vpt_embeddings_deep", "token_prefix", "token_suffix"} <= set(sdict)
+    tr.save_model(3, str(tmp_path), is_best=True)
+    with torch.no_grad():
+        tr.model.prompt_learner.ctx.zero_()
+    tr.load_model(str(tmp_path), epoch=3)
+    assert torch.equal(tr.model.prompt_learner.ctx.detach().cpu().float(), pp["ctx"])
+    tr.load_model(str(tmp_path))  # model-best.pth.tar
+
+
+def test_eval_path_and_text_feature_cache():
+    tr, fx, case, sd, image, pp, upt = _trainer("tiny_vpt_deep")
+    out1 = tr.model_inference(image.cuda())
+    out2 = tr.model_inference(image.cuda())  # second call reuses the cached (constant) text features
+    assert torch.equal(out1, out2)
+    from tests.helpers import rel_err
+    assert rel_err(out1.float().cpu(), fx["logits"]) < 3e-3
+    loader = [{"img": image, "label": fx["label"], "domain": torch.zeros(len(fx["label"]), dtype=torch.long)}]
+    tr.test_loader = loader
+    res = tr.test()
+    acc = 100.0 * float((fx["logits"].argmax(-1) == fx["label"]).float().mean())
+    assert abs(res["accuracy"] - acc) < 1e-6
