@@ -73,6 +73,9 @@ int mvlpt_fmha_fwd(const void* qkv, void* out, void* lse, int N, int L, int d, i
                    mvlpt_stream_t stream);
 int mvlpt_fmha_bwd(const void* qkv, const void* o, const void* d_o, const void* lse, void* dqkv, int N, int L, int d,
                    int heads, int causal, mvlpt_stream_t stream);
+/* Test hook: on=1 routes the two calls above to the legacy mma.sync (HMMA) kernels kept as an on-GPU cross-check of
+ * the tcgen05 kernels; returns the previous setting.  Never used by the product path. */
+int mvlpt_fmha_force_legacy(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm with fp32 statistics (clip/model.py:153-159).  x: fp32 residual stream [*, d]; y: fp16 [rows, d].

@@ -339,6 +339,15 @@ fmha_bwd_wmma_kernel(const __half* __restrict__ qkv, const __half* __restrict__ 
 
 }  // namespace
 
+static int g_force_legacy = 0;
+// Test hook: 1 routes mvlpt_fmha_fwd / mvlpt_fmha_bwd to the legacy HMMA kernels (kept as an on-GPU cross-check of
+// the tcgen05 kernels); returns the previous value.
+extern "C" int mvlpt_fmha_force_legacy(int on) {
+    const int old = g_force_legacy;
+    g_force_legacy = on;
+    return old;
+}
+
 extern "C" int mvlpt_fmha_fwd(const void* qkv, void* out, void* lse, int N, int L, int d, int heads, int causal,
                               mvlpt_stream_t stream) {
     if (!qkv || !out || !lse) return fail(MVLPT_EINVAL, "mvlpt_fmha_fwd: null argument");
@@ -349,7 +358,7 @@ extern "C" int mvlpt_fmha_fwd(const void* qkv, void* out, void* lse, int N, int 
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const float scale = 0.125f;  // 64^-1/2
-    if (!causal && fmha_sm100_supported(L)) return fmha_fwd_sm100(qkv, out, lse, N, L, d, heads, scale, s);
+    if (fmha_sm100_supported(L) && !g_force_legacy) return fmha_fwd_sm100(qkv, out, lse, N, L, d, heads, causal, s);
     const int Lp = (L + 15) / 16 * 16;
     const int ldS = (Lp + 8 > 72) ? Lp + 8 : 72;
     const size_t smem = (size_t)(64 + 2 * Lp) * LDH * 2 + (size_t)64 * ldS * 4;

@@ -1,11 +1,321 @@
-// tcgen05 attention forward for the image tower (non-causal, head width 64).  Placeholder until the TMEM
-// single-pass kernel lands: reports "unsupported" so mvlpt_fmha_fwd uses the HMMA kernel in fmha.cu.
+// tcgen05 attention FORWARD, head width 64, whole key range of a sequence in one pass (L <= 272).
+//
+// Replaces the inside of nn.MultiheadAttention as called at clip/model.py:181-183 (q*hd^-1/2, QK^T, causal -inf mask
+// of the text tower clip/model.py:324-330, softmax, PV).  One work unit = (sequence n, head h, 128-query tile):
+//
+//   TMA   : Q tile [128 x 64], K [Lp x 64], V [Lp x 64] straight out of the packed in_proj output [N, L, 3d] through a
+//           3-D tensor map (rows >= L are zero-filled by the TMA unit, so ragged L needs no padding in HBM)
+//   MMA 1 : S[128 x Lp] = Q . K^T        tcgen05.mma, fp32 accumulator in TMEM columns [0, Lp)
+//   warps : one thread per query row: row max, p = exp2(s*scale*log2e - max), row sum; P (fp16, unnormalised) goes
+//           to shared memory in the 128B-swizzled K-major layout the next MMA reads (it overwrites the dead Q/K tiles)
+//   MMA 2 : O[128 x 64] = P . V          V is consumed in place as an MN-major operand; O aliases S's TMEM columns
+//   store : O / rowsum -> fp16 -> swizzled staging tile -> TMA store (clips rows >= L); LSE (for the backward) -> HBM
+//
+// Persistent CTAs (192 threads: TMA warp, MMA warp, 4 softmax/epilogue warps), two per SM so that one CTA's
+// MUFU-bound softmax overlaps the other's loads and MMAs.  With head width 64 the kernel is exp-bound, not
+// MMA-bound (26.6k exps per 6.8 MFLOP tile): see DESIGN.md.
 #pragma once
 #include "common.cuh"
+#include "ptx_sm100.cuh"
 
 namespace mvlpt {
-inline bool fmha_sm100_supported(int /*L*/) { return false; }
-inline int fmha_fwd_sm100(const void*, void*, void*, int, int, int, int, float, cudaStream_t) {
-    return fail(MVLPT_ESHAPE, "fmha_fwd_sm100: not built");
+
+struct FmhaFwdParams {
+    int L, Lp, heads, q_tiles, num_tiles, causal;
+    float scale_log2e;  // hd^-1/2 * log2(e)
+    float scale;        // hd^-1/2
+    float* lse;         // [N, heads, L]
+    int box_h;          // rows per K/V TMA box (Lp / number of boxes)
+    uint32_t tmem_cols;
+    uint32_t off_v, off_o, off_bar;  // byte offsets inside the 1024-aligned dynamic shared memory
+};
+
+constexpr int kFmhaThreads = 192;
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kFmhaThreads, 2)
+fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                   const __grid_constant__ CUtensorMap tmap_out, const FmhaFwdParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sQ = smem;                    // [128 x 64] K-major SW128          (dead after MMA 1)
+    uint8_t* sK = smem + 16384;            // [Lp x 64]  K-major SW128          (dead after MMA 1)
+    uint8_t* sP = smem;                    // ceil(Lp/64) chunks of [128 x 64]  (aliases Q and K)
+    uint8_t* sV = smem + p.off_v;          // [Lp x 64]  rows = keys: MN-major B operand of MMA 2
+    uint8_t* sO = smem + p.off_o;          // [128 x 64] staging for the TMA store
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    uint64_t* qk_full = bars + 0;   // [2] by iteration parity
+    uint64_t* v_full = bars + 2;
+    uint64_t* s_full = bars + 4;
+    uint64_t* p_full = bars + 6;
+    uint64_t* o_full = bars + 8;
+    uint64_t* o_read = bars + 10;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Lp = p.Lp, d = p.heads * 64;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
+        tma_prefetch_desc(&tmap_out);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&qk_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], 128);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_read[i], 128);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, p.tmem_cols);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int qt = tile % p.q_tiles, nh = tile / p.q_tiles;
+                const int h = nh % p.heads, n = nh / p.heads;
+                // every barrier completes exactly once per tile: use k counts completions (parity (k)&1 of slot it&1)
+                const int slot = it & 1;
+                if (it > 0) mbar_wait(&o_full[(it - 1) & 1], ((it - 1) >> 1) & 1);  // P / K / V of the previous tile consumed
+                mbar_arrive_expect_tx(&qk_full[slot], 16384u + (uint32_t)Lp * 128u);
+                tma_load_3d(sQ, &tmap_q, &qk_full[slot], h * 64, qt * 128, n);
+                for (int r0 = 0; r0 < Lp; r0 += p.box_h)
+                    tma_load_3d(sK + r0 * 128, &tmap_kv, &qk_full[slot], d + h * 64, r0, n);
+                mbar_arrive_expect_tx(&v_full[slot], (uint32_t)Lp * 128u);
+                for (int r0 = 0; r0 < Lp; r0 += p.box_h)
+                    tma_load_3d(sV + r0 * 128, &tmap_kv, &v_full[slot], 2 * d + h * 64, r0, n);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            int it = 0;
+            for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+                const int slot = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
+                mbar_wait(&qk_full[slot], ph);
+                if (it > 0) mbar_wait(&o_read[(it - 1) & 1], ((it - 1) >> 1) & 1);  // O of the previous tile left TMEM
+                tc_fence_after();
+                // S = Q . K^T, N split in chunks of <= 256 columns
+                const uint64_t q_desc = umma_desc_k_sw128(smem_u32(sQ));
+                for (int n0 = 0; n0 < Lp; n0 += 256) {
+                    const int nn = (Lp - n0) < 256 ? (Lp - n0) : 256;
+                    const uint32_t idesc = umma_idesc_f16(128, (uint32_t)nn, 0, 0);
+                    const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK + n0 * 128));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_f16_ss(tmem_base + n0, q_desc + 2 * k, k_desc + 2 * k, idesc, k != 0);
+                }
+                umma_commit(&s_full[slot]);
+                // O = P . V
+                mbar_wait(&p_full[slot], ph);
+                mbar_wait(&v_full[slot], ph);
+                tc_fence_after();
+                const uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);  // B (V) is MN-major
+                const int ksteps = Lp / 16;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const uint64_t a_desc = umma_desc_k_sw128(smem_u32(sP + (kk >> 2) * 16384 + (kk & 3) * 32));
+                    const uint64_t b_desc = umma_desc_mn_sw128(smem_u32(sV + kk * 2048), 1024);
+                    umma_f16_ss(tmem_base, a_desc, b_desc, idesc_pv, kk != 0);
+                }
+                umma_commit(&o_full[slot]);
+            }
+        }
+    } else {
+        // ============================== softmax + epilogue (one query row per thread) ==============================
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;  // row inside the tile == TMEM lane
+        const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16);
+        const int etid = threadIdx.x - 64;  // 0..127
+        uint8_t* prow = sP + (r >> 3) * 1024 + (r & 7) * 128;
+        uint8_t* orow = sO + (r >> 3) * 1024 + (r & 7) * 128;
+        const int sw = r & 7;
+        int it = 0;
+        for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x, ++it) {
+            const int qt = tile % p.q_tiles, nh = tile / p.q_tiles;
+            const int h = nh % p.heads, n = nh / p.heads;
+            const int slot = it & 1;
+            const uint32_t ph = (it >> 1) & 1;
+            const int q = qt * 128 + r;
+            const bool warp_live = (qt * 128 + quarter * 32) < p.L;  // warp-uniform
+            const int lim = p.causal ? (q + 1 < p.L ? q + 1 : p.L) : p.L;  // valid keys: [0, lim)
+            mbar_wait(&s_full[slot], ph);
+            tc_fence_after();
+            float inv_sum = 0.f;
+            if (warp_live) {
+                // pass 1: row max of the raw scores over the valid keys
+                float m = -INFINITY;
+                for (int c0 = 0; c0 < Lp; c0 += 16) {
+                    uint32_t raw[16];
+                    tmem_ld_32x32b_x16(t_row + c0, raw);
+                    tmem_ld_wait();
+                    if (c0 + 16 <= lim) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(raw[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < lim) m = fmaxf(m, __uint_as_float(raw[j]));
+                    }
+                }
+                if (m == -INFINITY) m = 0.f;  // rows >= L (never stored)
+                const float m2 = m * p.scale_log2e;
+                // pass 2: p = exp2(s*scale*log2e - m2); unnormalised fp16 P -> smem; fp32 row sum
+                float sum = 0.f;
+                for (int c0 = 0; c0 < Lp; c0 += 16) {
+                    uint32_t raw[16];
+                    tmem_ld_32x32b_x16(t_row + c0, raw);
+                    tmem_ld_wait();
+                    float e[16];
+                    if (c0 + 16 <= lim) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) e[j] = ex2_approx(fmaf(__uint_as_float(raw[j]), p.scale_log2e, -m2));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            e[j] = (c0 + j < lim) ? ex2_approx(fmaf(__uint_as_float(raw[j]), p.scale_log2e, -m2)) : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sum += e[j];
+                    uint8_t* chunk = prow + (c0 >> 6) * 16384;
+                    const int u = (c0 & 63) >> 3;  // first of the two 16-byte units this group fills
+                    *reinterpret_cast<uint4*>(chunk + ((u ^ sw) << 4)) =
+                        make_uint4(pack_half2(e[0], e[1]), pack_half2(e[2], e[3]), pack_half2(e[4], e[5]), pack_half2(e[6], e[7]));
+                    *reinterpret_cast<uint4*>(chunk + (((u + 1) ^ sw) << 4)) =
+                        make_uint4(pack_half2(e[8], e[9]), pack_half2(e[10], e[11]), pack_half2(e[12], e[13]),
+                                   pack_half2(e[14], e[15]));
+                }
+                inv_sum = 1.f / sum;
+                if (q < p.L) p.lse[((size_t)n * p.heads + h) * p.L + q] = m * p.scale + __logf(sum);
+            }
+            fence_proxy_async_smem();  // P (generic-proxy stores) must be visible to the tensor core's async-proxy reads
+            tc_fence_before();
+            mbar_arrive(&p_full[slot]);
+
+            mbar_wait(&o_full[slot], ph);
+            tc_fence_after();
+            uint32_t o0[32], o1[32];
+            tmem_ld_32x32(t_row, o0);
+            tmem_ld_32x32(t_row + 32, o1);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&o_read[slot]);
+            // the previous tile's TMA store must have finished reading the staging tile
+            if (etid == 0) tma_store_wait_read<0>();
+            named_bar_sync(1, 128);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t* s = o0 + u * 8;
+                *reinterpret_cast<uint4*>(orow + ((u ^ sw) << 4)) = make_uint4(
+                    pack_half2(__uint_as_float(s[0]) * inv_sum, __uint_as_float(s[1]) * inv_sum),
+                    pack_half2(__uint_as_float(s[2]) * inv_sum, __uint_as_float(s[3]) * inv_sum),
+                    pack_half2(__uint_as_float(s[4]) * inv_sum, __uint_as_float(s[5]) * inv_sum),
+                    pack_half2(__uint_as_float(s[6]) * inv_sum, __uint_as_float(s[7]) * inv_sum));
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t* s = o1 + u * 8;
+                *reinterpret_cast<uint4*>(orow + (((u + 4) ^ sw) << 4)) = make_uint4(
+                    pack_half2(__uint_as_float(s[0]) * inv_sum, __uint_as_float(s[1]) * inv_sum),
+                    pack_half2(__uint_as_float(s[2]) * inv_sum, __uint_as_float(s[3]) * inv_sum),
+                    pack_half2(__uint_as_float(s[4]) * inv_sum, __uint_as_float(s[5]) * inv_sum),
+                    pack_half2(__uint_as_float(s[6]) * inv_sum, __uint_as_float(s[7]) * inv_sum));
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1, 128);
+            if (etid == 0) {
+                tma_store_3d(&tmap_out, sO, h * 64, qt * 128, n);
+                tma_store_commit();
+            }
+        }
+        if (etid == 0) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, p.tmem_cols);
+    }
+}
+
+inline bool fmha_sm100_supported(int L) { return L >= 1 && L <= 272; }
+
+inline int fmha_fwd_sm100(const void* qkv, void* out, void* lse, int N, int L, int d, int heads, int causal,
+                          cudaStream_t stream) {
+    const int Lp = (L + 15) / 16 * 16;
+    const int nbox = (Lp + 255) / 256;  // K / V arrive in nbox TMA boxes of Lp/nbox rows (a multiple of 8)
+    const int box_h = Lp / nbox;
+    if (box_h * nbox != Lp || (box_h % 8)) return fail(MVLPT_ESHAPE, "fmha_fwd_sm100: unsupported L=%d", L);
+    CUtensorMap tq, tkv, to;
+    {
+        uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)N};
+        uint64_t str[2] = {(uint64_t)3 * d * 2, (uint64_t)L * 3 * d * 2};
+        uint32_t box_q[3] = {64u, 128u, 1u};
+        uint32_t box_kv[3] = {64u, (uint32_t)box_h, 1u};
+        int rc = make_tmap_f16(&tq, qkv, 3, dims, str, box_q);
+        if (rc) return rc;
+        rc = make_tmap_f16(&tkv, qkv, 3, dims, str, box_kv);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)d, (uint64_t)L, (uint64_t)N};
+        uint64_t str[2] = {(uint64_t)d * 2, (uint64_t)L * d * 2};
+        uint32_t box[3] = {64u, 128u, 1u};
+        int rc = make_tmap_f16(&to, out, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    FmhaFwdParams p;
+    p.L = L;
+    p.Lp = Lp;
+    p.heads = heads;
+    p.q_tiles = (L + 127) / 128;
+    p.num_tiles = N * heads * p.q_tiles;
+    p.causal = causal;
+    p.scale = 0.125f;
+    p.scale_log2e = 0.125f * 1.4426950408889634f;
+    p.lse = static_cast<float*>(lse);
+    p.box_h = box_h;
+    p.tmem_cols = Lp <= 64 ? 64 : Lp <= 128 ? 128 : Lp <= 256 ? 256 : 512;
+    const uint32_t qk_bytes = 16384u + (uint32_t)Lp * 128u;
+    const uint32_t p_bytes = (uint32_t)((Lp + 63) / 64) * 16384u;
+    p.off_v = qk_bytes > p_bytes ? qk_bytes : p_bytes;
+    p.off_o = p.off_v + (uint32_t)Lp * 128u;
+    p.off_bar = p.off_o + 16384u;
+    const size_t smem = (size_t)p.off_bar + 128 + 1024;
+    static size_t attr = 0;
+    if (smem > attr) {
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const int per_sm = (smem * 2 <= 227 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
+    const int max_ctas = sm_count() * per_sm;
+    const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;
+    fmha_fwd_tc_kernel<<<grid, kFmhaThreads, smem, stream>>>(tq, tkv, to, p);
+    return launched("fmha_fwd_tc");
+}
+
 }  // namespace mvlpt

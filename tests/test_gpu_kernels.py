@@ -43,7 +43,8 @@ def test_gemm(M, N, K, act, resid, f32):
 
 
 @pytest.mark.parametrize("N,L,heads,causal", [(3, 197, 12, 0), (2, 205, 12, 0), (2, 50, 12, 0), (1, 257, 16, 0),
-                                              (5, 77, 8, 1), (4, 20, 8, 1), (2, 1, 2, 0), (2, 16, 2, 1)])
+                                              (5, 77, 8, 1), (4, 20, 8, 1), (2, 1, 2, 0), (2, 16, 2, 1), (40, 205, 12, 0),
+                                              (3, 130, 2, 1), (2, 64, 1, 0), (1, 272, 1, 0)])
 def test_fmha_fwd_bwd(N, L, heads, causal):
     from mvlpt_b200 import ops
     torch.manual_seed(1)
@@ -59,8 +60,8 @@ def test_fmha_fwd_bwd(N, L, heads, causal):
     p = s.softmax(-1)
     o = p @ v
     ref = o.permute(0, 2, 1, 3).reshape(N * L, d)
-    assert _rel(out.float(), ref) < 2e-3
-    assert _rel(lse, torch.logsumexp(s, -1)) < 1e-3
+    assert _rel(lse, torch.logsumexp(s, -1)) < 1e-3          # QK^T + softmax statistics
+    assert _rel(out.float(), ref) < 2e-3                      # PV
     do = (torch.randn(N * L, d, device="cuda") * 0.3).half()
     dqkv = torch.empty_like(qkv)
     ops.fmha_bwd(qkv, out, do, lse, dqkv, N, L, d, heads, causal)
