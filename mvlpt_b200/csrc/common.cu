@@ -31,6 +31,11 @@ static EncodeTiledFn get_encode() {
 
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box) {
+    return make_tmap(out, base, 0, rank, dims, strides_bytes, box);
+}
+
+int make_tmap(CUtensorMap* out, const void* base, int is_f32, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box) {
     EncodeTiledFn enc = get_encode();
     if (!enc) return fail(MVLPT_EARCH, "driver has no cuTensorMapEncodeTiled");
     if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return fail(MVLPT_EINVAL, "TMA base %p not 16-byte aligned", base);
@@ -48,7 +53,7 @@ int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* 
                                               (unsigned long long)gstr[i - 1]);
         }
     }
-    CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
+    CUresult r = enc(out, is_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx,
                      estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(MVLPT_ECUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", (int)r);

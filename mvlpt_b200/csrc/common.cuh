@@ -44,6 +44,9 @@ int require_sm100();
 // strides_bytes has rank-1 entries (stride of dim 1, dim 2, ...).
 int make_tmap_f16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box);
+// Same for fp32 (is_f32) or fp16 elements; the innermost box extent times the element size must be 128 bytes.
+int make_tmap(CUtensorMap* out, const void* base, int is_f32, int rank, const uint64_t* dims,
+              const uint64_t* strides_bytes, const uint32_t* box);
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 int sm_count();

@@ -12,6 +12,7 @@
 
 #include "common.cuh"
 #include "fmha_sm100.cuh"
+#include "fmha_bwd_sm100.cuh"
 
 using namespace nvcuda;
 using namespace mvlpt;
@@ -400,6 +401,8 @@ extern "C" int mvlpt_fmha_bwd(const void* qkv, const void* o, const void* d_o, c
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (fmha_bwd_sm100_supported(L) && !g_force_legacy)
+        return fmha_bwd_sm100(qkv, o, d_o, lse, dqkv, N, L, d, heads, causal, s);
     const int Lp = (L + 15) / 16 * 16;
     if (Lp <= 128) return launch_bwd<4>(qkv, o, d_o, lse, dqkv, N, L, Lp, d, heads, causal, s);
     if (Lp <= 224) return launch_bwd<7>(qkv, o, d_o, lse, dqkv, N, L, Lp, d, heads, causal, s);

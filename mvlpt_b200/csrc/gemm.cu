@@ -4,11 +4,11 @@
 
 using namespace mvlpt;
 
-template <int BN>
-static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const GemmEpilogue& ep,
-                       cudaStream_t stream) {
+template <int BN, bool F32>
+static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, void* aux_out, void* out,
+                       const GemmEpilogue& ep, cudaStream_t stream) {
     using Cfg = GemmCfg<BN>;
-    CUtensorMap ta, tw;
+    CUtensorMap ta, tw, to, tx;
     {
         uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
         uint64_t str[1] = {(uint64_t)d->lda * 2};
@@ -23,15 +23,30 @@ static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, c
         int rc = make_tmap_f16(&tw, W, 2, dims, str, box);
         if (rc) return rc;
     }
+    {
+        uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+        uint64_t str[1] = {(uint64_t)d->ld_out * (F32 ? 4 : 2)};
+        uint32_t box[2] = {F32 ? 32u : 64u, (uint32_t)kGemmBM};
+        int rc = make_tmap(&to, out, F32 ? 1 : 0, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    tx = to;
+    if (aux_out) {
+        uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+        uint64_t str[1] = {(uint64_t)d->ld_aux * 2};
+        uint32_t box[2] = {64u, (uint32_t)kGemmBM};
+        int rc = make_tmap_f16(&tx, aux_out, 2, dims, str, box);
+        if (rc) return rc;
+    }
     static bool attr_set = false;
     if (!attr_set) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                            Cfg::kSmemBytes));
         attr_set = true;
     }
     const int tiles = cdiv(d->M, kGemmBM) * cdiv(d->N, BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_f16_tn_kernel<BN><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, d->M, d->N, d->K, ep);
+    gemm_f16_tn_kernel<BN, F32><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tx, d->M, d->N, d->K, ep);
     return launched("gemm_f16_tn");
 }
 
@@ -45,10 +60,14 @@ extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W
     if (d->out_f32 ? (d->ld_out % 4) : (d->ld_out % 8))
         return fail(MVLPT_ESHAPE, "mvlpt_gemm: ld_out must be a multiple of %d", d->out_f32 ? 4 : 8);
     if ((reinterpret_cast<uintptr_t>(out) & 15) || (resid && (reinterpret_cast<uintptr_t>(resid) & 15)) ||
-        (bias && (reinterpret_cast<uintptr_t>(bias) & 15)))
-        return fail(MVLPT_EINVAL, "mvlpt_gemm: out/resid/bias must be 16-byte aligned");
+        (bias && (reinterpret_cast<uintptr_t>(bias) & 15)) || (aux_in && (reinterpret_cast<uintptr_t>(aux_in) & 15)) ||
+        (aux_out && (reinterpret_cast<uintptr_t>(aux_out) & 15)))
+        return fail(MVLPT_EINVAL, "mvlpt_gemm: out/resid/bias/aux must be 16-byte aligned");
     if (d->act < 0 || d->act > 2) return fail(MVLPT_EINVAL, "mvlpt_gemm: unknown act %d", d->act);
+    if (d->act != ACT_NONE && d->out_f32)
+        return fail(MVLPT_ESHAPE, "mvlpt_gemm: the QuickGELU epilogues produce fp16 (clear out_f32)");
     if (d->act == ACT_MUL_DQUICKGELU && !aux_in) return fail(MVLPT_EINVAL, "mvlpt_gemm: act 2 needs aux_in");
+    if (aux_out && d->act != ACT_QUICKGELU) return fail(MVLPT_EINVAL, "mvlpt_gemm: aux_out is the act-1 pre-activation");
     if ((aux_in || aux_out) && (d->ld_aux < d->N || (d->ld_aux % 8)))
         return fail(MVLPT_ESHAPE, "mvlpt_gemm: ld_aux must be >= N and a multiple of 8");
     if (resid && !d->out_f32) return fail(MVLPT_ESHAPE, "mvlpt_gemm: the residual stream is fp32; set out_f32");
@@ -57,16 +76,17 @@ extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W
 
     GemmEpilogue ep;
     ep.bias = static_cast<const __half*>(bias);
-    ep.aux_in = static_cast<const __half*>(aux_in);
-    ep.aux_out = static_cast<__half*>(aux_out);
+    ep.aux_in = d->act == ACT_MUL_DQUICKGELU ? static_cast<const __half*>(aux_in) : nullptr;
     ep.resid = static_cast<const float*>(resid);
-    ep.out = out;
+    ep.has_aux_out = aux_out != nullptr;
     ep.ld_out = d->ld_out;
     ep.ld_aux = d->ld_aux;
-    ep.out_f32 = d->out_f32;
     ep.act = d->act;
     ep.alpha = d->alpha;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (d->N <= 128) return launch_gemm<128>(d, A, W, ep, s);
-    return launch_gemm<256>(d, A, W, ep, s);
+    if (d->N <= 128)
+        return d->out_f32 ? launch_gemm<128, true>(d, A, W, aux_out, out, ep, s)
+                          : launch_gemm<128, false>(d, A, W, aux_out, out, ep, s);
+    return d->out_f32 ? launch_gemm<256, true>(d, A, W, aux_out, out, ep, s)
+                      : launch_gemm<256, false>(d, A, W, aux_out, out, ep, s);
 }

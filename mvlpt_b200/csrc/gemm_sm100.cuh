@@ -10,6 +10,12 @@
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue.
 // Pipelines: smem ring (full/empty mbarriers, kStages deep) and a 2-deep TMEM accumulator ring so the
 // epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Epilogue: one accumulator row per thread, 128 bytes of output per step (64 fp16 or 32 fp32 columns): TMEM ->
+// registers -> bias / QuickGELU / residual -> 128B-swizzled staging slab in shared memory -> TMA store (coalesced,
+// asynchronous, clips the ragged edges).  Row-wise INPUTS of the epilogue (fp32 residual stream, saved fp16
+// pre-activation) are read straight from global memory one step ahead into registers: a thread owns a whole
+// 128-byte line of them per step.
 #pragma once
 #include "ptx_sm100.cuh"
 
@@ -24,12 +30,10 @@ enum GemmAct : int {
 struct GemmEpilogue {
     const __half* bias;    // [N] or nullptr
     const __half* aux_in;  // [M, ld_aux] or nullptr   (ACT_MUL_DQUICKGELU)
-    __half* aux_out;       // [M, ld_aux] or nullptr   (pre-activation t saved for backward)
     const float* resid;    // [M, ld_out] fp32 or nullptr; may alias out
-    void* out;             // [M, ld_out] fp16 or fp32
+    int has_aux_out;       // pre-activation t saved through tmap_aux
     int ld_out;
     int ld_aux;
-    int out_f32;
     int act;
     float alpha;
 };
@@ -37,6 +41,7 @@ struct GemmEpilogue {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 192;
+constexpr int kGemmSlab = 16384;  // one staging slab: 128 rows x 128 bytes
 
 template <int BN>
 struct GemmCfg {
@@ -44,30 +49,42 @@ struct GemmCfg {
     static constexpr int kABytes = kGemmBM * kGemmBK * 2;
     static constexpr int kBBytes = BN * kGemmBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align slack*/ + 256 /*barriers*/;
+    static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kGemmSlab + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int kTmemCols = 2 * BN;
 };
 
-__device__ __forceinline__ float quickgelu_f(float t) {
-    float s = 1.f / (1.f + __expf(-1.702f * t));
-    return t * s;
+// sigmoid(z) = 0.5 + 0.5 tanh(z/2): one MUFU op instead of ex2 + rcp
+__device__ __forceinline__ float sigmoid_fast(float z) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * z));
+    return fmaf(0.5f, t, 0.5f);
 }
+__device__ __forceinline__ float quickgelu_f(float t) { return t * sigmoid_fast(1.702f * t); }
 __device__ __forceinline__ float dquickgelu_f(float t) {
-    float s = 1.f / (1.f + __expf(-1.702f * t));
-    return s * (1.f + 1.702f * t * (1.f - s));
+    const float s = sigmoid_fast(1.702f * t);
+    return s * fmaf(1.702f * t, 1.f - s, 1.f);
 }
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void gemm_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
-template <int BN>
+template <int BN, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
-gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w, int M, int N,
-                   int K, GemmEpilogue ep) {
+gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux, int M,
+                   int N, int K, GemmEpilogue ep) {
     using Cfg = GemmCfg<BN>;
     constexpr int kStages = Cfg::kStages;
+    constexpr int SW = OUT_F32 ? 32 : 64;  // output columns per 128-byte slab row
+    constexpr int kSteps = BN / SW;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * Cfg::kStageBytes);
+    uint8_t* smem_e = smem + kStages * Cfg::kStageBytes;  // 2 staging slabs
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_e + 2 * kGemmSlab);
     uint64_t* full_bar = bars;
     uint64_t* empty_bar = bars + kStages;
     uint64_t* tfull_bar = bars + 2 * kStages;
@@ -84,6 +101,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_a);
         tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_out);
+        if (ep.has_aux_out) tma_prefetch_desc(&tmap_aux);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -152,136 +171,175 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     } else {
         // ===================== epilogue (4 warps, one accumulator row per thread) =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
-        const int row_in_tile = quarter * 32 + lane;
+        const int r = quarter * 32 + lane;
+        const int etid = threadIdx.x - 64;
+        const bool issuer = (etid == 0);
+        const int sw = r & 7;
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const bool has_in = (ep.resid != nullptr) || (ep.aux_in != nullptr);
+        const int two = ep.has_aux_out;  // each step fills both slabs (out + saved pre-activation)
         int acc = 0;
         uint32_t acc_phase = 0;
+        uint32_t step_ctr = 0;
+
+        // row-wise epilogue input of one step: 128 bytes = 8 x 16 B of this thread's row (zero outside the matrix)
+        auto load_in = [&](int row, int col0, uint4 (&in)[8]) {
+            if (!has_in) return;
+            const bool row_ok = row < M;
+            if (OUT_F32) {
+                const float* src = ep.resid + (size_t)row * ep.ld_out + col0;
+                if (row_ok && col0 + 32 <= N) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) in[u] = *reinterpret_cast<const uint4*>(src + 4 * u);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        float f[4];
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) f[j] = (row_ok && col0 + 4 * u + j < N) ? src[4 * u + j] : 0.f;
+                        in[u] = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
+                                           __float_as_uint(f[3]));
+                    }
+                }
+            } else {
+                const __half* src = ep.aux_in + (size_t)row * ep.ld_aux + col0;
+                if (row_ok && col0 + 64 <= N) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) in[u] = *reinterpret_cast<const uint4*>(src + 8 * u);
+                } else {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        __half hh[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            hh[j] = (row_ok && col0 + 8 * u + j < N) ? src[8 * u + j] : __float2half(0.f);
+                        in[u] = *reinterpret_cast<uint4*>(hh);
+                    }
+                }
+            }
+        };
+
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * kGemmBM;
             const int n0 = (tile % n_tiles) * BN;
-            const int row = m0 + row_in_tile;
+            const int row = m0 + r;
+            uint4 in_cur[8], in_nxt[8];
+            load_in(row, n0, in_cur);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t raw[32];
-                tmem_ld_32x32(t_row + c * 32, raw);
-                tmem_ld_wait();
-                const int col0 = n0 + c * 32;
-                if (row < M && col0 < N) {
+            for (int s = 0; s < kSteps; ++s, ++step_ctr) {
+                const int col0 = n0 + s * SW;
+                if (s + 1 < kSteps) load_in(row, col0 + SW, in_nxt);
+                uint8_t* slab = smem_e + (two ? 0 : (step_ctr & 1) * kGemmSlab);
+                // the slab about to be overwritten must have been drained by its previous TMA store
+                if (issuer) {
+                    if (two) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+                }
+                gemm_bar_sync();
+                uint8_t* orow = slab + row_off;
+#pragma unroll
+                for (int hb = 0; hb < SW / 32; ++hb) {  // 32 accumulator columns at a time
+                    uint32_t raw[32];
+                    tmem_ld_32x32(t_row + s * SW + hb * 32, raw);
+                    tmem_ld_wait();
+                    if (s == kSteps - 1 && hb == SW / 32 - 1) {
+                        // last TMEM read of this tile: hand the accumulator back to the MMA warp
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+                    }
                     float v[32];
 #pragma unroll
                     for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * ep.alpha;
-                    const bool full = (col0 + 32 <= N);
+                    const int c0 = col0 + hb * 32;
                     if (ep.bias) {
-                        if (full) {
-                            const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + col0);
+                        if (c0 + 32 <= N) {
+                            const uint4* bp = reinterpret_cast<const uint4*>(ep.bias + c0);
 #pragma unroll
                             for (int q = 0; q < 4; ++q) {
-                                uint4 u = __ldg(bp + q);
+                                const uint4 u = __ldg(bp + q);
                                 const __half2* h2 = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    float2 f = __half22float2(h2[j]);
+                                    const float2 f = __half22float2(h2[j]);
                                     v[q * 8 + 2 * j] += f.x;
                                     v[q * 8 + 2 * j + 1] += f.y;
                                 }
                             }
                         } else {
+#pragma unroll
                             for (int j = 0; j < 32; ++j)
-                                if (col0 + j < N) v[j] += __half2float(ep.bias[col0 + j]);
+                                if (c0 + j < N) v[j] += __half2float(ep.bias[c0 + j]);
                         }
                     }
-                    if (ep.act == ACT_QUICKGELU) {
-                        if (ep.aux_out) {
-                            __half* ap = ep.aux_out + (size_t)row * ep.ld_aux + col0;
-                            if (full) {
+                    if (OUT_F32) {
+                        // fp32 slab row = 32 columns: unit u = columns 4u..4u+3 (+ residual)
+                        if (ep.resid) {
 #pragma unroll
-                                for (int q = 0; q < 4; ++q) {
-                                    uint4 u;
-                                    __half2* h2 = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                                    for (int j = 0; j < 4; ++j)
-                                        h2[j] = __floats2half2_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
-                                    reinterpret_cast<uint4*>(ap)[q] = u;
-                                }
-                            } else {
-                                for (int j = 0; j < 32; ++j)
-                                    if (col0 + j < N) ap[j] = __float2half_rn(v[j]);
+                            for (int u = 0; u < 8; ++u) {
+                                v[4 * u + 0] += __uint_as_float(in_cur[u].x);
+                                v[4 * u + 1] += __uint_as_float(in_cur[u].y);
+                                v[4 * u + 2] += __uint_as_float(in_cur[u].z);
+                                v[4 * u + 3] += __uint_as_float(in_cur[u].w);
                             }
                         }
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) v[j] = quickgelu_f(v[j]);
-                    } else if (ep.act == ACT_MUL_DQUICKGELU) {
-                        const __half* ap = ep.aux_in + (size_t)row * ep.ld_aux + col0;
-                        if (full) {
+                        for (int u = 0; u < 8; ++u)
+                            *reinterpret_cast<uint4*>(orow + ((u ^ sw) << 4)) =
+                                make_uint4(__float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
+                                           __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
+                    } else {
+                        // fp16 slab row = 64 columns: this half fills units 4*hb .. 4*hb+3 (8 columns each)
+                        if (ep.act == ACT_QUICKGELU) {
+                            if (two) {
+                                uint8_t* arow = orow + kGemmSlab;
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u = reinterpret_cast<const uint4*>(ap)[q];
-                                const __half2* h2 = reinterpret_cast<const __half2*>(&u);
+                                for (int u = 0; u < 4; ++u)
+                                    *reinterpret_cast<uint4*>(arow + (((4 * hb + u) ^ sw) << 4)) =
+                                        make_uint4(pack_h2(v[8 * u], v[8 * u + 1]), pack_h2(v[8 * u + 2], v[8 * u + 3]),
+                                                   pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7]));
+                            }
+#pragma unroll
+                            for (int j = 0; j < 32; ++j) v[j] = quickgelu_f(v[j]);
+                        } else if (ep.act == ACT_MUL_DQUICKGELU) {
+#pragma unroll
+                            for (int u = 0; u < 4; ++u) {
+                                const uint4 t4 = in_cur[4 * hb + u];
+                                const __half2* h2 = reinterpret_cast<const __half2*>(&t4);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
-                                    float2 f = __half22float2(h2[j]);
-                                    v[q * 8 + 2 * j] *= dquickgelu_f(f.x);
-                                    v[q * 8 + 2 * j + 1] *= dquickgelu_f(f.y);
+                                    const float2 f = __half22float2(h2[j]);
+                                    v[8 * u + 2 * j] *= dquickgelu_f(f.x);
+                                    v[8 * u + 2 * j + 1] *= dquickgelu_f(f.y);
                                 }
                             }
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < N) v[j] *= dquickgelu_f(__half2float(ap[j]));
                         }
-                    }
-                    if (ep.resid) {
-                        const float* rp = ep.resid + (size_t)row * ep.ld_out + col0;
-                        if (full) {
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                float4 f = reinterpret_cast<const float4*>(rp)[q];
-                                v[q * 4 + 0] += f.x;
-                                v[q * 4 + 1] += f.y;
-                                v[q * 4 + 2] += f.z;
-                                v[q * 4 + 3] += f.w;
-                            }
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < N) v[j] += rp[j];
-                        }
-                    }
-                    if (ep.out_f32) {
-                        float* op = reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ld_out + col0;
-                        if (full) {
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                reinterpret_cast<float4*>(op)[q] =
-                                    make_float4(v[q * 4], v[q * 4 + 1], v[q * 4 + 2], v[q * 4 + 3]);
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < N) op[j] = v[j];
-                        }
-                    } else {
-                        __half* op = reinterpret_cast<__half*>(ep.out) + (size_t)row * ep.ld_out + col0;
-                        if (full) {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint4 u;
-                                __half2* h2 = reinterpret_cast<__half2*>(&u);
-#pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    h2[j] = __floats2half2_rn(v[q * 8 + 2 * j], v[q * 8 + 2 * j + 1]);
-                                reinterpret_cast<uint4*>(op)[q] = u;
-                            }
-                        } else {
-                            for (int j = 0; j < 32; ++j)
-                                if (col0 + j < N) op[j] = __float2half_rn(v[j]);
-                        }
+                        for (int u = 0; u < 4; ++u)
+                            *reinterpret_cast<uint4*>(orow + (((4 * hb + u) ^ sw) << 4)) =
+                                make_uint4(pack_h2(v[8 * u], v[8 * u + 1]), pack_h2(v[8 * u + 2], v[8 * u + 3]),
+                                           pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7]));
                     }
                 }
+                fence_proxy_async_smem();
+                gemm_bar_sync();
+                if (issuer) {
+                    if (col0 < N) {
+                        tma_store_2d(&tmap_out, slab, col0, m0);
+                        if (two) tma_store_2d(&tmap_aux, slab + kGemmSlab, col0, m0);
+                    }
+                    tma_store_commit();  // one bulk group per step, even when empty: wait_group counts groups
+                }
+                if (s + 1 < kSteps) {
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) in_cur[u] = in_nxt[u];
+                }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (issuer) tma_store_wait_all();
     }
 
     tc_fence_before();

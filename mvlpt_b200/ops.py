@@ -89,6 +89,8 @@ def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid
         nbytes = 2.0 * (M * K + N * K) + (4.0 if out_f32 else 2.0) * M * N + (4.0 * M * N if resid is not None else 0.0) \
             + (2.0 * M * N if aux is not None else 0.0)
         PROFILER.end("gemm_f16_tn", t0, 2.0 * M * N * K, nbytes)
+        PROFILER.records.append((f"gemm[M={M},N={N},K={K},act={act},f32={out_f32},resid={int(resid is not None)}]",
+                                 *PROFILER.records[-1][1:]))
     return out
 
 
