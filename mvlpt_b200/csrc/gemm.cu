@@ -1,14 +1,39 @@
 // C-ABI entry for the tcgen05 GEMM (see include/mvlpt_sm100.h: mvlpt_gemm).
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "gemm_sm100.cuh"
 
 using namespace mvlpt;
 
-template <int BN, bool F32>
-static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, void* aux_out, void* out,
-                       const GemmEpilogue& ep, cudaStream_t stream) {
+// Operand-ring depth / output-ring slots.  Epilogues with a TMA-loaded input or a second output want a deep slab
+// ring; plain epilogues want the deepest operand ring.  MVLPT_GEMM_STAGES overrides the depth (tuning only).
+template <int BN>
+static void pick_pipeline(GemmEpilogue& ep) {
     using Cfg = GemmCfg<BN>;
-    CUtensorMap ta, tw, to, tx;
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("MVLPT_GEMM_STAGES");
+        forced = e ? atoi(e) : 0;
+    }
+    int stages = (ep.has_in || ep.has_aux_out) ? (BN == 256 ? 3 : 4) : (BN == 256 ? 4 : 5);
+    if (forced >= 2 && forced <= kGemmMaxStages && Cfg::slabs_for(forced) >= 2) stages = forced;
+    int slabs = Cfg::slabs_for(stages);
+    const int per = ep.has_aux_out ? 2 : 1;
+    int ring = slabs / per;
+    if (ring > kGemmMaxRing) ring = kGemmMaxRing;
+    ep.stages = stages;
+    ep.ring = ring;
+}
+
+template <int BN, bool F32>
+static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* in, void* aux_out, void* out,
+                       GemmEpilogue ep, cudaStream_t stream) {
+    using Cfg = GemmCfg<BN>;
+    pick_pipeline<BN>(ep);
+    if (ep.ring < 2) return fail(MVLPT_ESHAPE, "mvlpt_gemm: no room for the output ring");
+    const int smem_bytes = Cfg::smem_bytes(ep.stages, ep.ring * (ep.has_aux_out ? 2 : 1));
+    CUtensorMap ta, tw, to, tx, ti;
     {
         uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
         uint64_t str[1] = {(uint64_t)d->lda * 2};
@@ -31,6 +56,14 @@ static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, v
         if (rc) return rc;
     }
     tx = to;
+    ti = to;
+    if (in) {
+        uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+        uint64_t str[1] = {F32 ? (uint64_t)d->ld_out * 4 : (uint64_t)d->ld_aux * 2};
+        uint32_t box[2] = {F32 ? 32u : 64u, (uint32_t)kGemmBM};
+        int rc = make_tmap(&ti, in, F32 ? 1 : 0, 2, dims, str, box);
+        if (rc) return rc;
+    }
     if (aux_out) {
         uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
         uint64_t str[1] = {(uint64_t)d->ld_aux * 2};
@@ -38,15 +71,15 @@ static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, v
         int rc = make_tmap_f16(&tx, aux_out, 2, dims, str, box);
         if (rc) return rc;
     }
-    static bool attr_set = false;
-    if (!attr_set) {
+    static int attr = 0;
+    if (smem_bytes > attr) {
         MVLPT_CUDA_OK(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           Cfg::kSmemBytes));
-        attr_set = true;
+                                           smem_bytes));
+        attr = smem_bytes;
     }
     const int tiles = cdiv(d->M, kGemmBM) * cdiv(d->N, BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_f16_tn_kernel<BN, F32><<<grid, kGemmThreads, Cfg::kSmemBytes, stream>>>(ta, tw, to, tx, d->M, d->N, d->K, ep);
+    gemm_f16_tn_kernel<BN, F32><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tw, to, tx, ti, d->M, d->N, d->K, ep);
     return launched("gemm_f16_tn");
 }
 
@@ -76,17 +109,16 @@ extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W
 
     GemmEpilogue ep;
     ep.bias = static_cast<const __half*>(bias);
-    ep.aux_in = d->act == ACT_MUL_DQUICKGELU ? static_cast<const __half*>(aux_in) : nullptr;
-    ep.resid = static_cast<const float*>(resid);
+    const void* in = d->out_f32 ? resid : (d->act == ACT_MUL_DQUICKGELU ? aux_in : nullptr);
+    ep.has_in = in != nullptr;
     ep.has_aux_out = aux_out != nullptr;
-    ep.ld_out = d->ld_out;
-    ep.ld_aux = d->ld_aux;
     ep.act = d->act;
     ep.alpha = d->alpha;
+    ep.stages = ep.ring = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (d->N <= 128)
-        return d->out_f32 ? launch_gemm<128, true>(d, A, W, aux_out, out, ep, s)
-                          : launch_gemm<128, false>(d, A, W, aux_out, out, ep, s);
-    return d->out_f32 ? launch_gemm<256, true>(d, A, W, aux_out, out, ep, s)
-                      : launch_gemm<256, false>(d, A, W, aux_out, out, ep, s);
+        return d->out_f32 ? launch_gemm<128, true>(d, A, W, in, aux_out, out, ep, s)
+                          : launch_gemm<128, false>(d, A, W, in, aux_out, out, ep, s);
+    return d->out_f32 ? launch_gemm<256, true>(d, A, W, in, aux_out, out, ep, s)
+                      : launch_gemm<256, false>(d, A, W, in, aux_out, out, ep, s);
 }

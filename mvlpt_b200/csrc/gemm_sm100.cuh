@@ -8,14 +8,15 @@
 // weights [out, in]).
 //
 // Roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = epilogue.
-// Pipelines: smem ring (full/empty mbarriers, kStages deep) and a 2-deep TMEM accumulator ring so the
-// epilogue of tile i overlaps the MMAs of tile i+1.
+// Pipelines: operand ring in shared memory (full/empty mbarriers), a 2-deep TMEM accumulator ring so the epilogue of
+// tile i overlaps the MMAs of tile i+1, and a ring of 16 KB output slabs.
 //
 // Epilogue: one accumulator row per thread, 128 bytes of output per step (64 fp16 or 32 fp32 columns): TMEM ->
-// registers -> bias / QuickGELU / residual -> 128B-swizzled staging slab in shared memory -> TMA store (coalesced,
-// asynchronous, clips the ragged edges).  Row-wise INPUTS of the epilogue (fp32 residual stream, saved fp16
-// pre-activation) are read straight from global memory one step ahead into registers: a thread owns a whole
-// 128-byte line of them per step.
+// registers -> bias / QuickGELU / residual -> 128B-swizzled slab in shared memory -> TMA store (coalesced,
+// asynchronous, clips the ragged edges).  A row-wise INPUT of the epilogue (the fp32 residual stream, or the saved
+// fp16 pre-activation of the QuickGELU backward) is TMA-loaded into the very slab the result will leave from, a few
+// steps ahead, and updated in place — per-thread row reads from global memory would cost one L1 wavefront per
+// 16 bytes.
 #pragma once
 #include "ptx_sm100.cuh"
 
@@ -28,29 +29,32 @@ enum GemmAct : int {
 };
 
 struct GemmEpilogue {
-    const __half* bias;    // [N] or nullptr
-    const __half* aux_in;  // [M, ld_aux] or nullptr   (ACT_MUL_DQUICKGELU)
-    const float* resid;    // [M, ld_out] fp32 or nullptr; may alias out
-    int has_aux_out;       // pre-activation t saved through tmap_aux
-    int ld_out;
-    int ld_aux;
+    const __half* bias;  // [N] or nullptr
+    int has_in;          // a row-wise epilogue input arrives through tmap_in: the fp32 residual (fp32 output) or the
+                         // saved fp16 pre-activation (ACT_MUL_DQUICKGELU)
+    int has_aux_out;     // pre-activation t saved through tmap_aux (ACT_QUICKGELU while training)
     int act;
     float alpha;
+    int stages;          // depth of the operand ring
+    int ring;            // output ring slots (each 1 slab, or 2 when has_aux_out)
 };
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 192;
-constexpr int kGemmSlab = 16384;  // one staging slab: 128 rows x 128 bytes
+constexpr int kGemmSlab = 16384;  // 128 rows x 128 bytes
+constexpr int kGemmMaxStages = 6;
+constexpr int kGemmMaxRing = 6;
+constexpr int kGemmSmemBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
 
 template <int BN>
 struct GemmCfg {
-    static constexpr int kStages = (BN == 256) ? 4 : 6;
     static constexpr int kABytes = kGemmBM * kGemmBK * 2;
     static constexpr int kBBytes = BN * kGemmBK * 2;
     static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kSmemBytes = kStages * kStageBytes + 2 * kGemmSlab + 1024 /*align slack*/ + 256 /*barriers*/;
     static constexpr int kTmemCols = 2 * BN;
+    static constexpr int slabs_for(int stages) { return (kGemmSmemBudget - stages * kStageBytes) / kGemmSlab; }
+    static constexpr int smem_bytes(int stages, int slabs) { return stages * kStageBytes + slabs * kGemmSlab + 1024 + 256; }
 };
 
 // sigmoid(z) = 0.5 + 0.5 tanh(z/2): one MUFU op instead of ex2 + rcp
@@ -69,27 +73,39 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ void gemm_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read_n(int n) {
+    switch (n) {
+        case 0: tma_store_wait_read<0>(); break;
+        case 1: tma_store_wait_read<1>(); break;
+        case 2: tma_store_wait_read<2>(); break;
+        case 3: tma_store_wait_read<3>(); break;
+        case 4: tma_store_wait_read<4>(); break;
+        default: tma_store_wait_read<5>(); break;
+    }
+}
 
 template <int BN, bool OUT_F32>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
-                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux, int M,
-                   int N, int K, GemmEpilogue ep) {
+                   const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
+                   const __grid_constant__ CUtensorMap tmap_in, int M, int N, int K, GemmEpilogue ep) {
     using Cfg = GemmCfg<BN>;
-    constexpr int kStages = Cfg::kStages;
     constexpr int SW = OUT_F32 ? 32 : 64;  // output columns per 128-byte slab row
     constexpr int kSteps = BN / SW;
+    const int kStages = ep.stages;
+    const int per = ep.has_aux_out ? 2 : 1;  // slabs per ring slot
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + kStages * Cfg::kABytes;
-    uint8_t* smem_e = smem + kStages * Cfg::kStageBytes;  // 2 staging slabs
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_e + 2 * kGemmSlab);
+    uint8_t* smem_e = smem + kStages * Cfg::kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_e + ep.ring * per * kGemmSlab);
     uint64_t* full_bar = bars;
-    uint64_t* empty_bar = bars + kStages;
-    uint64_t* tfull_bar = bars + 2 * kStages;
-    uint64_t* tempty_bar = bars + 2 * kStages + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+    uint64_t* empty_bar = bars + kGemmMaxStages;
+    uint64_t* tfull_bar = bars + 2 * kGemmMaxStages;
+    uint64_t* tempty_bar = tfull_bar + 2;
+    uint64_t* in_full = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + kGemmMaxRing);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -103,6 +119,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_out);
         if (ep.has_aux_out) tma_prefetch_desc(&tmap_aux);
+        if (ep.has_in) tma_prefetch_desc(&tmap_in);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
             mbar_init(&empty_bar[s], 1);
@@ -111,6 +128,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
             mbar_init(&tfull_bar[s], 1);
             mbar_init(&tempty_bar[s], 4);
         }
+        for (int s = 0; s < kGemmMaxRing; ++s) mbar_init(&in_full[s], 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -172,72 +190,47 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
         // ===================== epilogue (4 warps, one accumulator row per thread) =====================
         const int quarter = warp & 3;  // TMEM lane quarter this warp may access
         const int r = quarter * 32 + lane;
-        const int etid = threadIdx.x - 64;
-        const bool issuer = (etid == 0);
+        const bool issuer = (threadIdx.x == 64);
         const int sw = r & 7;
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-        const bool has_in = (ep.resid != nullptr) || (ep.aux_in != nullptr);
-        const int two = ep.has_aux_out;  // each step fills both slabs (out + saved pre-activation)
+        const bool has_in = ep.has_in != 0;
+        const bool two = ep.has_aux_out != 0;
+        const int R = ep.ring;
         int acc = 0;
         uint32_t acc_phase = 0;
-        uint32_t step_ctr = 0;
-
-        // row-wise epilogue input of one step: 128 bytes = 8 x 16 B of this thread's row (zero outside the matrix)
-        auto load_in = [&](int row, int col0, uint4 (&in)[8]) {
-            if (!has_in) return;
-            const bool row_ok = row < M;
-            if (OUT_F32) {
-                const float* src = ep.resid + (size_t)row * ep.ld_out + col0;
-                if (row_ok && col0 + 32 <= N) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) in[u] = *reinterpret_cast<const uint4*>(src + 4 * u);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        float f[4];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) f[j] = (row_ok && col0 + 4 * u + j < N) ? src[4 * u + j] : 0.f;
-                        in[u] = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]),
-                                           __float_as_uint(f[3]));
-                    }
-                }
-            } else {
-                const __half* src = ep.aux_in + (size_t)row * ep.ld_aux + col0;
-                if (row_ok && col0 + 64 <= N) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) in[u] = *reinterpret_cast<const uint4*>(src + 8 * u);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) {
-                        __half hh[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            hh[j] = (row_ok && col0 + 8 * u + j < N) ? src[8 * u + j] : __float2half(0.f);
-                        in[u] = *reinterpret_cast<uint4*>(hh);
-                    }
-                }
-            }
+        int g = 0;  // steps done by this CTA
+        const int my_tiles = (int)blockIdx.x < num_tiles ? (num_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+        const int total_steps = my_tiles * kSteps;
+        // TMA load of the epilogue input of step gg into its ring slot (issuer thread only)
+        auto issue_in = [&](int gg) {
+            if (gg >= total_steps) return;
+            const int t = blockIdx.x + (gg / kSteps) * gridDim.x;
+            const int mm = (t / n_tiles) * kGemmBM, nn = (t % n_tiles) * BN + (gg % kSteps) * SW;
+            const int slot = gg % R;
+            mbar_arrive_expect_tx(&in_full[slot], kGemmSlab);
+            tma_load_2d(smem_e + slot * kGemmSlab, &tmap_in, &in_full[slot], nn, mm);
         };
+        if (has_in && issuer)
+            for (int gg = 0; gg < R - 1; ++gg) issue_in(gg);
 
         for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
             const int m0 = (tile / n_tiles) * kGemmBM;
             const int n0 = (tile % n_tiles) * BN;
-            const int row = m0 + r;
-            uint4 in_cur[8], in_nxt[8];
-            load_in(row, n0, in_cur);
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN;
 #pragma unroll 1
-            for (int s = 0; s < kSteps; ++s, ++step_ctr) {
+            for (int s = 0; s < kSteps; ++s, ++g) {
                 const int col0 = n0 + s * SW;
-                if (s + 1 < kSteps) load_in(row, col0 + SW, in_nxt);
-                uint8_t* slab = smem_e + (two ? 0 : (step_ctr & 1) * kGemmSlab);
-                // the slab about to be overwritten must have been drained by its previous TMA store
-                if (issuer) {
-                    if (two) tma_store_wait_read<0>(); else tma_store_wait_read<1>();
+                const int slot = g % R;
+                uint8_t* slab = smem_e + slot * per * kGemmSlab;
+                if (has_in) {
+                    mbar_wait(&in_full[slot], (uint32_t)(g / R) & 1);  // input landed (implies the slot was drained)
+                } else {
+                    // the slot about to be overwritten must have been drained by the TMA store of step g - R
+                    if (issuer) tma_store_wait_read_n(R - 1);
+                    gemm_bar_sync();
                 }
-                gemm_bar_sync();
                 uint8_t* orow = slab + row_off;
 #pragma unroll
                 for (int hb = 0; hb < SW / 32; ++hb) {  // 32 accumulator columns at a time
@@ -275,21 +268,20 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         }
                     }
                     if (OUT_F32) {
-                        // fp32 slab row = 32 columns: unit u = columns 4u..4u+3 (+ residual)
-                        if (ep.resid) {
+                        // fp32 slab row = 32 columns: unit u = columns 4u..4u+3; the residual is already in the slab
 #pragma unroll
-                            for (int u = 0; u < 8; ++u) {
-                                v[4 * u + 0] += __uint_as_float(in_cur[u].x);
-                                v[4 * u + 1] += __uint_as_float(in_cur[u].y);
-                                v[4 * u + 2] += __uint_as_float(in_cur[u].z);
-                                v[4 * u + 3] += __uint_as_float(in_cur[u].w);
+                        for (int u = 0; u < 8; ++u) {
+                            uint4* dst = reinterpret_cast<uint4*>(orow + ((u ^ sw) << 4));
+                            if (has_in) {
+                                const uint4 x = *dst;
+                                v[4 * u + 0] += __uint_as_float(x.x);
+                                v[4 * u + 1] += __uint_as_float(x.y);
+                                v[4 * u + 2] += __uint_as_float(x.z);
+                                v[4 * u + 3] += __uint_as_float(x.w);
                             }
+                            *dst = make_uint4(__float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
+                                              __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
                         }
-#pragma unroll
-                        for (int u = 0; u < 8; ++u)
-                            *reinterpret_cast<uint4*>(orow + ((u ^ sw) << 4)) =
-                                make_uint4(__float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
-                                           __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
                     } else {
                         // fp16 slab row = 64 columns: this half fills units 4*hb .. 4*hb+3 (8 columns each)
                         if (ep.act == ACT_QUICKGELU) {
@@ -306,7 +298,7 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         } else if (ep.act == ACT_MUL_DQUICKGELU) {
 #pragma unroll
                             for (int u = 0; u < 4; ++u) {
-                                const uint4 t4 = in_cur[4 * hb + u];
+                                const uint4 t4 = *reinterpret_cast<const uint4*>(orow + (((4 * hb + u) ^ sw) << 4));
                                 const __half2* h2 = reinterpret_cast<const __half2*>(&t4);
 #pragma unroll
                                 for (int j = 0; j < 4; ++j) {
@@ -331,10 +323,12 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
                         if (two) tma_store_2d(&tmap_aux, slab + kGemmSlab, col0, m0);
                     }
                     tma_store_commit();  // one bulk group per step, even when empty: wait_group counts groups
-                }
-                if (s + 1 < kSteps) {
-#pragma unroll
-                    for (int u = 0; u < 8; ++u) in_cur[u] = in_nxt[u];
+                    if (has_in) {
+                        // the slot of step g-1 is drained once every group but the newest has been read:
+                        // refill it with the input of step g-1+R
+                        tma_store_wait_read<1>();
+                        issue_in(g - 1 + R);
+                    }
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }

@@ -57,29 +57,48 @@ ok &= run(64, 128, 128, bias=False)
 ok &= run(33, 104, 72, alpha=3.5, out_f32=True)
 ok &= run(50432, 768, 768, resid=True, out_f32=True)
 
-# timing: the four block linears at B=256, L=197
-def bench(M, N, K, iters=20):
+# timing: the block linears at B=256, L=197 in every epilogue mode the engine uses
+def bench(M, N, K, iters=20, act=0, resid=False, f32=False, aux_out=False):
     A = (torch.randn(M, K, device=dev) * 0.5).half(); W = (torch.randn(N, K, device=dev) * 0.05).half()
-    b = torch.zeros(N, device=dev).half(); out = torch.empty(M, N, device=dev, dtype=torch.half)
-    d = _lib.GemmDesc(M, N, K, K, K, N, N, 0, 0, 1.0)
+    b = torch.zeros(N, device=dev).half()
+    out = torch.empty(M, N, device=dev, dtype=torch.float32 if f32 else torch.half)
+    r = torch.randn(M, N, device=dev) if resid else None
+    aux_in = torch.randn(M, N, device=dev).half() if act == 2 else None
+    aux_o = torch.empty(M, N, device=dev, dtype=torch.half) if aux_out else None
+    d = _lib.GemmDesc(M, N, K, K, K, N, N, act, int(f32), 1.0)
     stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    call = lambda: L.mvlpt_gemm(ctypes.byref(d), ptr(A), ptr(W), ptr(b), ptr(aux_in), ptr(aux_o), ptr(r), ptr(out), stream)
     for _ in range(3):
-        L.mvlpt_gemm(ctypes.byref(d), ptr(A), ptr(W), ptr(b), None, None, None, ptr(out), stream)
+        _lib.check(call(), "gemm")
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
-        L.mvlpt_gemm(ctypes.byref(d), ptr(A), ptr(W), ptr(b), None, None, None, ptr(out), stream)
+        call()
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / iters
-    e0.record()
-    for _ in range(iters):
-        torch.nn.functional.linear(A, W, b)
-    e1.record(); torch.cuda.synchronize()
-    ms_t = e0.elapsed_time(e1) / iters
     tf = 2 * M * N * K / ms / 1e9
-    print(f"bench M={M} N={N} K={K}: ours {ms:.3f} ms = {tf:.0f} TFLOP/s ; torch {ms_t:.3f} ms = {2*M*N*K/ms_t/1e9:.0f} TFLOP/s", flush=True)
+    print(f"bench M={M} N={N} K={K} act={act} resid={int(resid)} f32={int(f32)} aux_out={int(aux_out)}: {ms:.3f} ms = {tf:.0f} TFLOP/s", flush=True)
 
-for (M, N, K) in [(50432, 2304, 768), (50432, 768, 768), (50432, 3072, 768), (50432, 768, 3072), (8192, 8192, 8192)]:
-    bench(M, N, K)
+import os
+print("MVLPT_GEMM_STAGES =", os.environ.get("MVLPT_GEMM_STAGES"))
+bench(50432, 2304, 768)
+bench(50432, 768, 768)
+bench(50432, 768, 768, resid=True, f32=True)
+bench(50432, 768, 3072, resid=True, f32=True)
+bench(50432, 3072, 768, act=1)
+bench(50432, 3072, 768, act=1, aux_out=True)
+bench(50432, 3072, 768, act=2)
+bench(50432, 768, 3072)
+bench(7700, 2048, 512, act=1, aux_out=True)
+bench(7700, 512, 2048, resid=True, f32=True)
+bench(7700, 512, 512, resid=True, f32=True)
+bench(8192, 8192, 8192)
+A = torch.randn(8192, 8192, device=dev).half(); W = torch.randn(8192, 8192, device=dev).half()
+for _ in range(3): torch.nn.functional.linear(A, W)
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(10): torch.nn.functional.linear(A, W)
+e1.record(); torch.cuda.synchronize()
+print(f"torch (cuBLAS) 8192^3: {2*8192**3/(e0.elapsed_time(e1)/10)/1e9:.0f} TFLOP/s")
 print("ALL OK" if ok else "FAILURES")
 sys.exit(0 if ok else 1)
