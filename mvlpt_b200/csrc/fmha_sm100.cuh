@@ -17,6 +17,7 @@
 #pragma once
 #include "common.cuh"
 #include "ptx_sm100.cuh"
+#include <stdlib.h>
 
 namespace mvlpt {
 
@@ -262,11 +263,330 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// Forward, current generation (Lp <= 256): one work unit = one (sequence, head); its ceil(L/128) query tiles share
+// one K / V load.  Differences from the kernel above:
+//   * two S accumulators in TMEM (256 columns each) and two softmax warp groups: tile t lives in buffer t & 1, so the
+//     tensor pipe computes S of the next tile / PV of the previous one while a group is in its MUFU-bound softmax;
+//   * a group is 8 warps = 2 per TMEM lane quarter; the pair splits the key columns of a row and exchanges the partial
+//     row maxima through shared memory, so 4 warps per scheduler keep the MUFU pipe busy;
+//   * P never touches shared memory: it is written back in place over S as packed fp16 (tcgen05.st) and consumed by
+//     the PV MMA as a tensor-memory A operand; O accumulates in free columns of the same buffer;
+//   * the row sum is a 16-column MMA of P against a tile of ones, i.e. the sum of exactly the
+//     fp16 values PV uses (ex2.approx.f16x2 was tried: it lowers to two MUFU.EX2.F16, no MUFU saving);
+//   * Q / K / V of the next unit stream into a second shared-memory stage while this unit computes.
+// 576 threads: TMA warp, MMA warp, 2 x 8 softmax/epilogue warps; all 512 TMEM columns, one CTA per SM.
+struct FmhaFwd2Params {
+    int L, Lp, heads, QT, num_units, causal;
+    float scale_log2e, scale;
+    float* lse;  // [N, heads, L]
+    uint32_t stage_bytes, off_k, off_v, off_o, off_ones, off_max, off_bar;
+    // TMEM columns inside a 256-column buffer.  The two warps of a lane quarter split the key columns at `csplit`;
+    // each writes its fp16 P in place over ITS OWN part of S (keys [0, csplit) -> columns [0, csplit/2), keys
+    // [csplit, Lp) -> columns [csplit, csplit + (Lp-csplit)/2)), so neither overwrites scores the other still reads.
+    // O (64 columns) and the row sum (16 columns) go where no P lives.
+    int csplit, o_col, sum_col;
+};
+
+constexpr int kFmhaFwd2Threads = 576;
+constexpr int kFmhaFwd2Group = 256;  // threads of one softmax group
+
+__global__ void __launch_bounds__(kFmhaFwd2Threads, 1)
+fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
+                    const __grid_constant__ CUtensorMap tmap_out, const FmhaFwd2Params p) {
+    extern __shared__ __align__(1024) uint8_t smem_fwd2[];
+    uint8_t* smem = smem_fwd2;
+    uint8_t* sOnes = smem + p.off_ones;                          // [16 x 64] fp16 ones (B operand of the row-sum MMA)
+    float* sMax = reinterpret_cast<float*>(smem + p.off_max);    // [2 groups][2 halves][128 rows] partial row maxima
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+    uint64_t* qk_full = bars + 0;     // [2] per shared-memory stage
+    uint64_t* v_full = bars + 2;      // [2]
+    uint64_t* stage_free = bars + 4;  // [2] every MMA reading the stage has completed
+    uint64_t* s_full = bars + 6;      // [2] per TMEM buffer
+    uint64_t* p_full = bars + 8;      // [2]
+    uint64_t* o_full = bars + 10;     // [2]
+    uint64_t* o_read = bars + 12;     // [2] O has left TMEM: the buffer may be overwritten
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int Lp = p.Lp, d = p.heads * 64, QT = p.QT;
+    const int my_units = (int)blockIdx.x < p.num_units ? (p.num_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int T = my_units * QT;  // tiles this CTA processes; tile t = (unit t / QT, query tile t % QT)
+
+    if (warp == 0 && lane == 0) {
+        if (smem_u32(smem) & 1023u) {
+            printf("mvlpt: fmha_fwd dynamic shared memory is not 1024-byte aligned\n");
+            __trap();
+        }
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_kv);
+        tma_prefetch_desc(&tmap_out);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&qk_full[i], 1);
+            mbar_init(&v_full[i], 1);
+            mbar_init(&stage_free[i], 1);
+            mbar_init(&s_full[i], 1);
+            mbar_init(&p_full[i], kFmhaFwd2Group);
+            mbar_init(&o_full[i], 1);
+            mbar_init(&o_read[i], kFmhaFwd2Group);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    if (warp >= 2 && threadIdx.x - 64 < 128)  // 2 KB of fp16 1.0
+        reinterpret_cast<uint4*>(sOnes)[threadIdx.x - 64] = make_uint4(0x3C003C00u, 0x3C003C00u, 0x3C003C00u, 0x3C003C00u);
+    fence_proxy_async_smem();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ============================== TMA producer ==============================
+        if (lane == 0) {
+            for (int u = 0; u < my_units; ++u) {
+                const int unit = blockIdx.x + u * gridDim.x;
+                const int h = unit % p.heads, n = unit / p.heads;
+                const int s = u & 1;
+                uint8_t* st = smem + s * p.stage_bytes;
+                if (u >= 2) mbar_wait(&stage_free[s], (uint32_t)((u >> 1) - 1) & 1);
+                mbar_arrive_expect_tx(&qk_full[s], (uint32_t)QT * 16384u + (uint32_t)Lp * 128u);
+                for (int qt = 0; qt < QT; ++qt) tma_load_3d(st + qt * 16384, &tmap_q, &qk_full[s], h * 64, qt * 128, n);
+                tma_load_3d(st + p.off_k, &tmap_kv, &qk_full[s], d + h * 64, 0, n);
+                mbar_arrive_expect_tx(&v_full[s], (uint32_t)Lp * 128u);
+                tma_load_3d(st + p.off_v, &tmap_kv, &v_full[s], 2 * d + h * 64, 0, n);
+            }
+        }
+    } else if (warp == 1) {
+        // ============================== MMA issuer ==============================
+        if (lane == 0) {
+            const uint32_t idesc_s = umma_idesc_f16(128, (uint32_t)Lp, 0, 0);
+            const uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);  // B (V) is MN-major
+            const uint32_t idesc_sum = umma_idesc_f16(128, 16, 0, 0);
+            const uint64_t ones_desc = umma_desc_k_sw128(smem_u32(sOnes));
+            auto issue_s = [&](int t) {
+                const int u = t / QT, qt = t - u * QT, s = u & 1, b = t & 1;
+                uint8_t* st = smem + s * p.stage_bytes;
+                if (qt == 0) mbar_wait(&qk_full[s], (uint32_t)(u >> 1) & 1);
+                if (t >= 2) mbar_wait(&o_read[b], (uint32_t)((t >> 1) - 1) & 1);  // O of tile t-2 left the buffer
+                tc_fence_after();
+                const uint64_t q_desc = umma_desc_k_sw128(smem_u32(st + qt * 16384));
+                const uint64_t k_desc = umma_desc_k_sw128(smem_u32(st + p.off_k));
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    umma_f16_ss(tmem_base + b * 256, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
+                umma_commit(&s_full[b]);
+            };
+            if (T > 0) issue_s(0);
+            for (int t = 0; t < T; ++t) {
+                if (t + 1 < T) issue_s(t + 1);
+                const int u = t / QT, qt = t - u * QT, s = u & 1, b = t & 1;
+                const uint32_t sV = smem_u32(smem + s * p.stage_bytes + p.off_v);
+                mbar_wait(&p_full[b], (uint32_t)(t >> 1) & 1);
+                if (qt == 0) mbar_wait(&v_full[s], (uint32_t)(u >> 1) & 1);
+                tc_fence_after();
+                const uint32_t tb = tmem_base + b * 256;
+                const int ksteps = Lp / 16;
+                for (int kk = 0; kk < ksteps; ++kk) {
+                    const int k0 = kk * 16;  // first key of this step -> where its P columns live
+                    const uint32_t pa = tb + (k0 < p.csplit ? (k0 >> 1) : p.csplit + ((k0 - p.csplit) >> 1));
+                    umma_f16_ts(tb + p.o_col, pa, umma_desc_mn_sw128(sV + kk * 2048, 1024), idesc_pv, kk != 0);
+                    umma_f16_ts(tb + p.sum_col, pa, ones_desc, idesc_sum, kk != 0);
+                }
+                umma_commit(&o_full[b]);
+                if (qt == QT - 1) umma_commit(&stage_free[s]);
+            }
+        }
+    } else {
+        // ============================== softmax + epilogue: group g owns TMEM buffer g ==============================
+        const int quarter = warp & 3;           // TMEM lane quarter this warp may access
+        const int g = (warp - 2) >> 3;          // warps 2..9 -> group 0, 10..17 -> group 1
+        const int half = ((warp - 2) >> 2) & 1; // which part of the key columns / of the O columns
+        const int r = quarter * 32 + lane;      // row inside the tile == TMEM lane
+        const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + g * 256;
+        const bool leader = ((warp - 2) & 7) == 0 && lane == 0;  // issues this group's TMA stores
+        uint8_t* sO = smem + p.off_o + g * 16384;
+        uint8_t* orow = sO + (r >> 3) * 1024 + (r & 7) * 128;
+        float* my_max = sMax + (g * 2 + half) * 128 + r;
+        const float* other_max = sMax + (g * 2 + (half ^ 1)) * 128 + r;
+        const int sw = r & 7;
+        const float sl2 = p.scale_log2e;
+        const int csplit = p.csplit;  // key columns [0, csplit) -> half 0, [csplit, Lp) -> half 1
+        const int cb = half ? csplit : 0, ce = half ? Lp : csplit;
+        const uint32_t p_row = t_row + (half ? csplit - (csplit >> 1) : 0);  // + (c0 >> 1) = where P of key c0 goes
+        for (int t = g; t < T; t += 2) {
+            const int u = t / QT, qt = t - u * QT;
+            const int unit = blockIdx.x + u * gridDim.x;
+            const int h = unit % p.heads, n = unit / p.heads;
+            const uint32_t ph = (uint32_t)(t >> 1) & 1;
+            const int q = qt * 128 + r;
+            const bool warp_live = (qt * 128 + quarter * 32) < p.L;  // warp-uniform, same for both halves of a quarter
+            const int lim = p.causal ? (q + 1 < p.L ? q + 1 : p.L) : p.L;  // valid keys: [0, lim)
+            mbar_wait(&s_full[g], ph);
+            tc_fence_after();
+            float m = -INFINITY;
+            if (warp_live) {
+                // pass 1: max of the raw scores over this warp's share of the valid keys
+                for (int c0 = cb; c0 < ce; c0 += 16) {
+                    uint32_t raw[16];
+                    tmem_ld_32x32b_x16(t_row + c0, raw);
+                    tmem_ld_wait();
+                    if (c0 + 16 <= lim) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(raw[j]));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            if (c0 + j < lim) m = fmaxf(m, __uint_as_float(raw[j]));
+                    }
+                }
+                *my_max = m;
+            }
+            named_bar_sync(1 + g, kFmhaFwd2Group);  // also orders the previous tile's staging reads (see below)
+            if (warp_live) {
+                m = fmaxf(m, *other_max);
+                if (m == -INFINITY) m = 0.f;  // rows >= L (never stored)
+                const float m2 = m * sl2;
+                // pass 2: p = exp2(s*scale*log2e - m2) as packed fp16, back into TMEM over S
+                for (int c0 = cb; c0 < ce; c0 += 16) {
+                    uint32_t raw[16];
+                    tmem_ld_32x32b_x16(t_row + c0, raw);
+                    tmem_ld_wait();
+                    uint32_t pk[8];
+                    if (c0 + 16 <= lim) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            pk[j] = pack_half2(ex2_approx(fmaf(__uint_as_float(raw[2 * j]), sl2, -m2)),
+                                               ex2_approx(fmaf(__uint_as_float(raw[2 * j + 1]), sl2, -m2)));
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float e0 = (c0 + 2 * j < lim) ? ex2_approx(fmaf(__uint_as_float(raw[2 * j]), sl2, -m2)) : 0.f;
+                            const float e1 = (c0 + 2 * j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(raw[2 * j + 1]), sl2, -m2)) : 0.f;
+                            pk[j] = pack_half2(e0, e1);
+                        }
+                    }
+                    tmem_st_32x32b_x8(p_row + (c0 >> 1), pk);
+                }
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&p_full[g]);
+
+            mbar_wait(&o_full[g], ph);
+            tc_fence_after();
+            uint32_t o[32], sm[16];
+            tmem_ld_32x32(t_row + p.o_col + 32 * half, o);
+            tmem_ld_32x32b_x16(t_row + p.sum_col, sm);
+            tmem_ld_wait();
+            tc_fence_before();
+            mbar_arrive(&o_read[g]);
+            const float sum = __uint_as_float(sm[0]);
+            const float inv_sum = 1.f / sum;
+            if (half == 0 && warp_live && q < p.L) p.lse[((size_t)n * p.heads + h) * p.L + q] = m * p.scale + __logf(sum);
+            // this group's previous TMA store must have finished reading the staging tile
+            if (leader) tma_store_wait_read<0>();
+            named_bar_sync(1 + g, kFmhaFwd2Group);
+#pragma unroll
+            for (int uu = 0; uu < 4; ++uu) {
+                const uint32_t* s = o + uu * 8;
+                *reinterpret_cast<uint4*>(orow + (((uu + 4 * half) ^ sw) << 4)) = make_uint4(
+                    pack_half2(__uint_as_float(s[0]) * inv_sum, __uint_as_float(s[1]) * inv_sum),
+                    pack_half2(__uint_as_float(s[2]) * inv_sum, __uint_as_float(s[3]) * inv_sum),
+                    pack_half2(__uint_as_float(s[4]) * inv_sum, __uint_as_float(s[5]) * inv_sum),
+                    pack_half2(__uint_as_float(s[6]) * inv_sum, __uint_as_float(s[7]) * inv_sum));
+            }
+            fence_proxy_async_smem();
+            named_bar_sync(1 + g, kFmhaFwd2Group);
+            if (leader) {
+                tma_store_3d(&tmap_out, sO, h * 64, qt * 128, n);
+                tma_store_commit();
+            }
+        }
+        if (leader) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+inline int fmha_fwd2_sm100(const void* qkv, void* out, void* lse, int N, int L, int d, int heads, int causal,
+                           cudaStream_t stream) {
+    const int Lp = (L + 15) / 16 * 16;  // <= 256: K / V arrive in one TMA box each
+    CUtensorMap tq, tkv, to;
+    {
+        uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)N};
+        uint64_t str[2] = {(uint64_t)3 * d * 2, (uint64_t)L * 3 * d * 2};
+        uint32_t box_q[3] = {64u, 128u, 1u};
+        uint32_t box_kv[3] = {64u, (uint32_t)Lp, 1u};
+        int rc = make_tmap_f16(&tq, qkv, 3, dims, str, box_q);
+        if (rc) return rc;
+        rc = make_tmap_f16(&tkv, qkv, 3, dims, str, box_kv);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[3] = {(uint64_t)d, (uint64_t)L, (uint64_t)N};
+        uint64_t str[2] = {(uint64_t)d * 2, (uint64_t)L * d * 2};
+        uint32_t box[3] = {64u, 128u, 1u};
+        int rc = make_tmap_f16(&to, out, 3, dims, str, box);
+        if (rc) return rc;
+    }
+    FmhaFwd2Params p;
+    p.L = L;
+    p.Lp = Lp;
+    p.heads = heads;
+    p.QT = (L + 127) / 128;
+    p.num_units = N * heads;
+    p.causal = causal;
+    p.scale = 0.125f;
+    p.scale_log2e = 0.125f * 1.4426950408889634f;
+    p.lse = static_cast<float*>(lse);
+    const uint32_t kv = (uint32_t)((Lp * 128 + 1023) / 1024 * 1024);
+    p.off_k = (uint32_t)p.QT * 16384u;
+    p.off_v = p.off_k + kv;
+    p.stage_bytes = p.off_v + kv;
+    p.off_o = 2u * p.stage_bytes;
+    p.off_ones = p.off_o + 32768u;
+    p.off_max = p.off_ones + 2048u;
+    p.off_bar = p.off_max + 2048u;
+    {
+        p.csplit = ((Lp >> 4) + 1) / 2 * 16;
+        const int p1_end = p.csplit + (Lp - p.csplit) / 2;
+        const int tail0 = (p1_end + 31) / 32 * 32, gap0 = (p.csplit / 2 + 31) / 32 * 32;
+        const int tail = 256 - tail0, gap = p.csplit - gap0;
+        if (tail >= 80) { p.o_col = tail0; p.sum_col = tail0 + 64; }
+        else if (tail >= 64 && gap >= 16) { p.o_col = tail0; p.sum_col = gap0; }
+        else if (gap >= 64 && tail >= 16) { p.o_col = gap0; p.sum_col = tail0; }
+        else if (gap >= 80) { p.o_col = gap0; p.sum_col = gap0 + 64; }
+        else return fail(MVLPT_ESHAPE, "fmha_fwd2_sm100: no TMEM room for O at L=%d", L);
+    }
+    const size_t smem = (size_t)p.off_bar + 128;
+    if (smem > 227 * 1024) return fail(MVLPT_ESHAPE, "fmha_fwd2_sm100: L=%d needs %zu bytes of shared memory", L, smem);
+    static size_t attr = 0;
+    if (smem > attr) {
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr = smem;
+    }
+    const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
+    fmha_fwd_tc2_kernel<<<grid, kFmhaFwd2Threads, smem, stream>>>(tq, tkv, to, p);
+    return launched("fmha_fwd_tc2");
+}
+
 inline bool fmha_sm100_supported(int L) { return L >= 1 && L <= 272; }
 
 inline int fmha_fwd_sm100(const void* qkv, void* out, void* lse, int N, int L, int d, int heads, int causal,
                           cudaStream_t stream) {
     const int Lp = (L + 15) / 16 * 16;
+    // two stages of Q/K/V fit shared memory up to 240 keys
+    if (Lp <= 240 && !getenv("MVLPT_FMHA_FWD_V1")) return fmha_fwd2_sm100(qkv, out, lse, N, L, d, heads, causal, stream);
     const int nbox = (Lp + 255) / 256;  // K / V arrive in nbox TMA boxes of Lp/nbox rows (a multiple of 8)
     const int box_h = Lp / nbox;
     if (box_h * nbox != Lp || (box_h % 8)) return fail(MVLPT_ESHAPE, "fmha_fwd_sm100: unsupported L=%d", L);
