@@ -24,7 +24,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
     "--expt-relaxed-constexpr",
     "-DMVLPT_BUILDING_LIB",
-]
+] + os.environ.get("MVLPT_NVCC_EXTRA", "").split()  # e.g. -DMVLPT_FMHA_DBG for the in-kernel trace (tools/ only)
 
 
 def _sources():

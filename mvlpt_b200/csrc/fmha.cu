@@ -408,3 +408,15 @@ extern "C" int mvlpt_fmha_bwd(const void* qkv, const void* o, const void* d_o, c
     if (Lp <= 224) return launch_bwd<7>(qkv, o, d_o, lse, dqkv, N, L, Lp, d, heads, causal, s);
     return launch_bwd<9>(qkv, o, d_o, lse, dqkv, N, L, Lp, d, heads, causal, s);
 }
+
+#ifdef MVLPT_FMHA_DBG
+// Debug builds only: copy out and reset the in-kernel timestamp trace of the backward kernel (not part of the ABI).
+extern "C" int mvlpt_dbg_fmha_trace(unsigned long long* out, int* counts) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_fmha_dbg, sizeof(unsigned long long) * 2 * 2048);
+    cudaMemcpyFromSymbol(counts, g_fmha_dbg_n, sizeof(int) * 2);
+    int zero[2] = {0, 0};
+    cudaMemcpyToSymbol(g_fmha_dbg_n, zero, sizeof(zero));
+    return 0;
+}
+#endif

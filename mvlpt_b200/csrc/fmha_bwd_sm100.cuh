@@ -1,38 +1,67 @@
 // tcgen05 attention BACKWARD, head width 64, L <= 256 (autograd of F.multi_head_attention_forward as
-// called at clip/model.py:181-183).  One work unit = one (sequence n, head h); the whole head lives on one SM:
+// called at clip/model.py:181-183).  One work unit = one (sequence n, head h); the whole head lives on one SM.
 //
-//   TMA   : Q, dO (ceil(L/128) tiles of [128 x 64]) and K, V (same number of 128-row chunks) out of the packed
-//           [N, L, 3d] / [N, L, d] tensors through 3-D maps (rows >= L zero-filled).  Every tile is a stack of
-//           128-byte rows with the 128B swizzle, which serves BOTH operand majors: K-major when the contraction runs
-//           over the head width, MN-major when it runs over the rows — so no transposed copy of anything is ever made.
-//           The loads of a unit form two groups (tile/chunk 0 and tile/chunk 1), each with its own full/free
-//           barriers: group 0 of the NEXT unit streams in while the last iteration of this unit still computes.
-//   loop key chunk kc (128 keys) x query tile qt (128 queries):
-//     MMA : S  = Q_qt . K_kc^T      -> TMEM [  0,128)         dP = dO_qt . V_kc^T  -> TMEM [128,256)
-//     thr : 8 row warps = 2 per TMEM lane quarter; the pair splits the key columns of the chunk.  Per query row:
-//           P = exp2(S*scale*log2e - lse*log2e),  dS = P o (dP - D),  D = rowsum(dO o O);
-//           P and dS (fp16) -> swizzled shared memory
-//     MMA : dV_kc += P^T . dO_qt   -> TMEM [256,320)    (A = P  read MN-major, contraction over queries)
-//           dK_kc += dS^T . Q_qt   -> TMEM [320,384)    (A = dS read MN-major)
-//           dQ_qt += dS . K_kc     -> TMEM [384+64 qt, ..)   (A = dS read K-major, B = K read MN-major)
-//   after the last qt of a chunk: dK_kc * hd^-1/2, dV_kc -> fp16 -> staging -> TMA store; after the last chunk: dQ.
+// The score tile is computed TRANSPOSED (keys on the TMEM lanes, queries on the columns), in steps of
+// (key chunk kc of 128 keys) x (query half-tile qh of 64 queries), double-buffered in TMEM:
 //
-// 320 threads: TMA warp, MMA warp, 8 row warps.  TMEM: all 512 columns, hence one CTA per SM.
+//   MMA-1 : S^T  = K_kc . Q_qh^T   -> TMEM buffer b, columns [0,64)      dP^T = V_kc . dO_qh^T -> columns [64,128)
+//   rows  : 8 warps = 2 per TMEM lane quarter (the pair splits the 64 query columns); thread = one key:
+//             P^T = exp2(S^T*scale*log2e - lse[q]*log2e),   dS^T = P^T o (dP^T - D[q]),   D = rowsum(dO o O)
+//           P^T and dS^T go back IN PLACE into TMEM as packed fp16 (tcgen05.st) — they are the A operands of
+//             dV_kc += P^T  . dO_qh      -> TMEM [256,320)        dK_kc += dS^T . Q_qh  -> TMEM [320,384)
+//           (tensor-memory A operand, no shared-memory traffic); dS^T also goes to shared memory (128-byte swizzled
+//           rows = keys), from where a whole 128-query tile is consumed MN-major by
+//             dQ_qt += dS . K_kc         -> TMEM [384+64 qt, ..)   once both of its halves are there.
+//   While the row warps work on step j, the tensor pipe runs MMA-1 of step j+1 (other TMEM buffer) and the dV/dK/dQ
+//   MMAs of step j-1; shared-memory dS is double-buffered per query tile.  No barrier is needed for either reuse: the
+//   MMAs of one thread execute in issue order, and a later tcgen05.commit covers every earlier MMA.
+//   after the last qh of a chunk: dK_kc * hd^-1/2, dV_kc -> fp16 -> staging -> TMA store; after the last chunk: dQ.
+//
+//   TMA   : Q, dO (128-row tiles) and K, V (128-row chunks) out of the packed [N, L, 3d] / [N, L, d] tensors through
+//           3-D maps (rows >= L zero-filled).  Every tile is a stack of 128-byte rows with the 128B swizzle, which
+//           serves BOTH operand majors (K-major when the contraction runs over the head width, MN-major when it runs
+//           over the rows), so no transposed copy of anything is ever made.  The loads of a unit form two groups
+//           (tile/chunk 0 and 1) with their own full/free barriers: group 0 of the NEXT unit streams in while the last
+//           steps of this unit still compute.
+//
+// 448 threads: TMA warp, MMA warp, 8 row warps, 4 epilogue warps.  TMEM: all 512 columns, hence one CTA per SM.
 #pragma once
 #include "fmha_sm100.cuh"
 
 namespace mvlpt {
 
 struct FmhaBwdParams {
-    int L, Lp, heads, d, QT, KC, causal, num_units, box_h;
+    int L, Lp, heads, d, QT, KC, NQH, causal, num_units;
     float scale_log2e;   // hd^-1/2 * log2(e)
     const float* lse;    // [N, heads, L]
     const __half* o;     // [N, L, d]
     const __half* d_o;   // [N, L, d]
-    uint32_t off_do, off_k, off_v, off_p, off_ds, off_stage, off_row, off_bar;
+    uint32_t off_do, off_k, off_v, off_ds, off_stage, off_row, off_bar;
 };
 
-constexpr int kFmhaBwdThreads = 320;
+#ifdef MVLPT_FMHA_DBG
+// Debug build only (tools/gpu_fmha_trace.py): CTA 0 records (tag, globaltimer) pairs of its MMA thread (stream 0) and of
+// the first row thread (stream 1).
+__device__ unsigned long long g_fmha_dbg[2][2048];
+__device__ int g_fmha_dbg_n[2];
+#define FMHA_DBG(stream, tag)                                                              \
+    do {                                                                                   \
+        if (blockIdx.x == 0) {                                                             \
+            const int _i = g_fmha_dbg_n[stream];                                           \
+            if (_i < 1024) {                                                               \
+                g_fmha_dbg[stream][2 * _i] = (unsigned long long)(tag);                    \
+                g_fmha_dbg[stream][2 * _i + 1] = globaltimer_ns();                         \
+                g_fmha_dbg_n[stream] = _i + 1;                                             \
+            }                                                                              \
+        }                                                                                  \
+    } while (0)
+#else
+#define FMHA_DBG(stream, tag) \
+    do {                      \
+    } while (0)
+#endif
+
+constexpr int kFmhaBwdThreads = 448;
 constexpr int kFmhaBwdRowThreads = 256;
 
 __global__ void __launch_bounds__(kFmhaBwdThreads, 1)
@@ -43,25 +72,25 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint8_t* smem = smem_bwd;
     uint8_t* sQ = smem;                 // QT x [128 x 64]
     uint8_t* sdO = smem + p.off_do;     // QT x [128 x 64]
-    uint8_t* sK = smem + p.off_k;       // KC x [box_h x 64]
-    uint8_t* sV = smem + p.off_v;       // KC x [box_h x 64]
-    uint8_t* sP = smem + p.off_p;       // 2 chunks (64 keys each) of [128 queries x 128 B]
-    uint8_t* sdS = smem + p.off_ds;     // same shape
+    uint8_t* sK = smem + p.off_k;       // KC x [128 x 64]
+    uint8_t* sV = smem + p.off_v;       // KC x [128 x 64]
+    uint8_t* sdS = smem + p.off_ds;     // 2 buffers x 2 chunks (64 queries each) of [128 keys x 128 B]
     uint8_t* sSt = smem + p.off_stage;  // 2 x [128 x 64] staging for the TMA stores
     float* sD = reinterpret_cast<float*>(smem + p.off_row);  // [256] rowsum(dO o O)
     float* sL2 = sD + 256;                                   // [256] lse * log2(e)
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
-    uint64_t* ld_full = bars + 0;  // [2] load group g landed
-    uint64_t* g_free = bars + 2;   // [2] every MMA reading load group g of this unit has completed
-    uint64_t* s_full = bars + 4;
-    uint64_t* p_ready = bars + 5;
-    uint64_t* acc_full = bars + 6;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 7);
+    uint64_t* ld_full = bars + 0;   // [2] load group g landed
+    uint64_t* g_free = bars + 2;    // [2] every MMA reading load group g of this unit has completed
+    uint64_t* st_full = bars + 4;   // [2] S^T / dP^T of a step are in TMEM buffer b
+    uint64_t* p_ready = bars + 6;   // [2] P^T / dS^T of a step are written (TMEM + shared memory)
+    uint64_t* acc_full = bars + 8;  // dK / dV of a key chunk (and every earlier MMA) complete
+    uint64_t* acc_free = bars + 9;  // the epilogue warps have read the accumulators of a key chunk out of TMEM
+    uint64_t* d_full = bars + 10;   // per-query statistics (D, lse) of a unit are in shared memory
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int Lp = p.Lp, d = p.d, QT = p.QT, KC = p.KC;
-    const uint32_t kv_chunk = (uint32_t)p.box_h * 128u;  // bytes of one K (or V) chunk in shared memory
-    constexpr uint32_t kColS = 0, kColDP = 128, kColDV = 256, kColDK = 320, kColDQ = 384;
+    const int Lp = p.Lp, d = p.d, QT = p.QT, KC = p.KC, NQH = p.NQH;
+    constexpr uint32_t kColDV = 256, kColDK = 320, kColDQ = 384;
 
     if (warp == 0 && lane == 0) {
         if (smem_u32(smem) & 1023u) {
@@ -75,10 +104,12 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         for (int g = 0; g < 2; ++g) {
             mbar_init(&ld_full[g], 1);
             mbar_init(&g_free[g], 1);
+            mbar_init(&st_full[g], 1);
+            mbar_init(&p_ready[g], kFmhaBwdRowThreads);
         }
-        mbar_init(s_full, 1);
-        mbar_init(p_ready, kFmhaBwdRowThreads);
         mbar_init(acc_full, 1);
+        mbar_init(acc_free, 128);
+        mbar_init(d_full, 128);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -98,225 +129,340 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 const int h = unit % p.heads, n = unit / p.heads;
                 for (int g = 0; g < QT; ++g) {  // QT == KC: group g = {Q_g, dO_g, K_g, V_g}
                     if (it > 0) mbar_wait(&g_free[g], (uint32_t)(it - 1) & 1);
-                    mbar_arrive_expect_tx(&ld_full[g], 32768u + 2u * kv_chunk);
+                    mbar_arrive_expect_tx(&ld_full[g], 65536u);
                     tma_load_3d(sQ + g * 16384, &tmap_q, &ld_full[g], h * 64, g * 128, n);
+                    tma_load_3d(sK + g * 16384, &tmap_q, &ld_full[g], d + h * 64, g * 128, n);
                     tma_load_3d(sdO + g * 16384, &tmap_do, &ld_full[g], h * 64, g * 128, n);
-                    tma_load_3d(sK + g * kv_chunk, &tmap_kv, &ld_full[g], d + h * 64, g * 128, n);
-                    tma_load_3d(sV + g * kv_chunk, &tmap_kv, &ld_full[g], 2 * d + h * 64, g * 128, n);
+                    tma_load_3d(sV + g * 16384, &tmap_q, &ld_full[g], 2 * d + h * 64, g * 128, n);
                 }
             }
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            int it = 0;
-            uint32_t gi = 0;  // iterations issued so far (parity of p_ready)
-            auto issue_s_dp = [&](int kc, int qt) {
+        // The WHOLE warp runs the control flow (warp-uniform values stay in uniform registers, which is what the
+        // tcgen05 instructions take); one elected lane issues the MMAs and commits.
+        const bool leader = elect_one();
+        const uint32_t idesc_acc = umma_idesc_f16(128, 64, 0, 1);  // A from TMEM (K-major), B MN-major
+        const uint32_t idesc_dq = umma_idesc_f16(128, 64, 1, 1);   // A = dS MN-major, B = K MN-major
+        // descriptors of the tile bases; an operand at byte offset `off` inside a tile is desc + (off >> 4)
+        const uint64_t dK_k = umma_desc_k_sw128(smem_u32(sK)), dQ_k = umma_desc_k_sw128(smem_u32(sQ));
+        const uint64_t dV_k = umma_desc_k_sw128(smem_u32(sV)), ddO_k = umma_desc_k_sw128(smem_u32(sdO));
+        const uint64_t ddO_mn = umma_desc_mn_sw128(smem_u32(sdO), 1024), dQ_mn = umma_desc_mn_sw128(smem_u32(sQ), 1024);
+        const uint64_t dK_mn = umma_desc_mn_sw128(smem_u32(sK), 1024), ddS_mn = umma_desc_mn_sw128(smem_u32(sdS), 16384);
+        uint32_t gi = 0;   // steps issued so far by this CTA (TMEM buffer = gi & 1)
+        uint32_t tci = 0;  // (kc, query tile) pairs so far (dS shared-memory buffer = tci & 1)
+        uint32_t gph = 0;  // key chunks started so far (parity of acc_free)
+        // MMA-1 of step (kc, qh) into TMEM buffer b
+        auto issue_st = [&](int kc, int qh, uint32_t b) {
+            const int nq = (Lp - qh * 64) < 64 ? (Lp - qh * 64) : 64;
+            const uint32_t idesc = umma_idesc_f16(128, (uint32_t)nq, 0, 0);
+            const uint64_t k_desc = dK_k + (uint32_t)(kc * (16384 >> 4)), q_desc = dQ_k + (uint32_t)(qh * (8192 >> 4));
+            const uint64_t v_desc = dV_k + (uint32_t)(kc * (16384 >> 4)), do_desc = ddO_k + (uint32_t)(qh * (8192 >> 4));
+            const uint32_t tb = tmem_base + b * 128;
+            if (leader) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_ss(tb, k_desc + 2 * k, q_desc + 2 * k, idesc, k != 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_f16_ss(tb + 64, v_desc + 2 * k, do_desc + 2 * k, idesc, k != 0);
+                umma_commit(&st_full[b]);
+            }
+            __syncwarp();
+        };
+        int it = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+            if (leader) FMHA_DBG(0, 1);
+            mbar_wait(&ld_full[0], (uint32_t)it & 1);
+            tc_fence_after();
+            if (leader) FMHA_DBG(0, 2);
+            issue_st(0, 0, gi & 1);
+            bool g1_ready = false;
+            for (int kc = 0; kc < KC; ++kc) {
                 const int nk = (Lp - kc * 128) < 128 ? (Lp - kc * 128) : 128;
-                const uint32_t idesc = umma_idesc_f16(128, (uint32_t)nk, 0, 0);
-                const uint64_t q_desc = umma_desc_k_sw128(smem_u32(sQ + qt * 16384));
-                const uint64_t k_desc = umma_desc_k_sw128(smem_u32(sK + kc * kv_chunk));
-                const uint64_t do_desc = umma_desc_k_sw128(smem_u32(sdO + qt * 16384));
-                const uint64_t v_desc = umma_desc_k_sw128(smem_u32(sV + kc * kv_chunk));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + kColS, q_desc + 2 * k, k_desc + 2 * k, idesc, k != 0);
-#pragma unroll
-                for (int k = 0; k < 4; ++k) umma_f16_ss(tmem_base + kColDP, do_desc + 2 * k, v_desc + 2 * k, idesc, k != 0);
-                umma_commit(s_full);
-            };
-            for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
-                mbar_wait(&ld_full[0], (uint32_t)it & 1);
-                tc_fence_after();
-                issue_s_dp(0, 0);
-                for (int kc = 0; kc < KC; ++kc) {
-                    const int nk = (Lp - kc * 128) < 128 ? (Lp - kc * 128) : 128;
-                    for (int qt = 0; qt < QT; ++qt) {
-                        const int nq = (Lp - qt * 128) < 128 ? (Lp - qt * 128) : 128;  // live query rows (multiple of 16)
-                        mbar_wait(p_ready, gi & 1);
-                        ++gi;
-                        tc_fence_after();
-                        // dV_kc (+)= P^T . dO_qt ; dK_kc (+)= dS^T . Q_qt      contraction over the nq queries
-                        const uint32_t idesc_t = umma_idesc_f16(128, 64, 1, 1);
-                        for (int kk = 0; kk < nq / 16; ++kk) {
-                            const uint64_t a_p = umma_desc_mn_sw128(smem_u32(sP + kk * 2048), 16384);
-                            const uint64_t b_do = umma_desc_mn_sw128(smem_u32(sdO + qt * 16384 + kk * 2048), 1024);
-                            umma_f16_ss(tmem_base + kColDV, a_p, b_do, idesc_t, (qt | kk) != 0);
-                        }
-                        for (int kk = 0; kk < nq / 16; ++kk) {
-                            const uint64_t a_ds = umma_desc_mn_sw128(smem_u32(sdS + kk * 2048), 16384);
-                            const uint64_t b_q = umma_desc_mn_sw128(smem_u32(sQ + qt * 16384 + kk * 2048), 1024);
-                            umma_f16_ss(tmem_base + kColDK, a_ds, b_q, idesc_t, (qt | kk) != 0);
-                        }
-                        // dQ_qt (+)= dS . K_kc      contraction over the nk keys
-                        const uint32_t idesc_q = umma_idesc_f16(128, 64, 0, 1);
-                        for (int kk = 0; kk < nk / 16; ++kk) {
-                            const uint64_t a_ds = umma_desc_k_sw128(smem_u32(sdS + (kk >> 2) * 16384 + (kk & 3) * 32));
-                            const uint64_t b_k = umma_desc_mn_sw128(smem_u32(sK + kc * kv_chunk + kk * 2048), 1024);
-                            umma_f16_ss(tmem_base + kColDQ + qt * 64, a_ds, b_k, idesc_q, (kc | kk) != 0);
-                        }
-                        if (qt == QT - 1) umma_commit(acc_full);
-                        // load group 0 (Q_0, dO_0, K_0, V_0) is last read by iteration (KC-1, 0); group 1 by the last one
-                        if (kc == KC - 1 && qt == 0) umma_commit(&g_free[0]);
-                        if (kc == KC - 1 && qt == 1) umma_commit(&g_free[1]);
-                        const int nqt = (qt + 1 == QT) ? 0 : qt + 1;
-                        const int nkc = (qt + 1 == QT) ? kc + 1 : kc;
+                for (int qh = 0; qh < NQH; ++qh, ++gi) {
+                    const uint32_t b = gi & 1;
+                    const int nq = (Lp - qh * 64) < 64 ? (Lp - qh * 64) : 64;
+                    // MMA-1 of the next step first: it overlaps the row warps' work on this one
+                    {
+                        const int nqh = (qh + 1 == NQH) ? 0 : qh + 1;
+                        const int nkc = (qh + 1 == NQH) ? kc + 1 : kc;
                         if (nkc < KC) {
-                            if (kc == 0 && qt == 0) {  // first use of load group 1 (only reachable when QT == KC == 2)
+                            if (!g1_ready && (nkc > 0 || nqh >= 2)) {  // first touch of load group 1
                                 mbar_wait(&ld_full[1], (uint32_t)it & 1);
                                 tc_fence_after();
+                                g1_ready = true;
                             }
-                            issue_s_dp(nkc, nqt);
+                            issue_st(nkc, nqh, b ^ 1);
                         }
                     }
+                    if (leader) FMHA_DBG(0, 3);
+                    mbar_wait(&p_ready[b], (gi >> 1) & 1);
+                    if (qh == 0) {
+                        // the first dV / dK MMA of a chunk overwrites what the epilogue warps read (dQ likewise, later)
+                        if (gph > 0) mbar_wait(acc_free, (gph - 1) & 1);
+                        ++gph;
+                    }
+                    tc_fence_after();
+                    if (leader) FMHA_DBG(0, 4);
+                    // dV_kc (+)= P^T . dO_qh ; dK_kc (+)= dS^T . Q_qh      contraction over the nq queries
+                    const uint32_t tb = tmem_base + b * 128;
+                    const uint64_t b_do = ddO_mn + (uint32_t)(qh * (8192 >> 4)), b_q = dQ_mn + (uint32_t)(qh * (8192 >> 4));
+                    const int nkk = nq >> 4;
+                    if (leader) {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk) {
+                            if (kk < nkk) {
+                                const uint32_t pc = (uint32_t)(kk * 8 + (kk >= 2 ? 16 : 0));  // see the row warps' layout
+                                umma_f16_ts(tmem_base + kColDV, tb + pc, b_do + kk * (2048 >> 4), idesc_acc, (qh | kk) != 0);
+                                umma_f16_ts(tmem_base + kColDK, tb + 64 + pc, b_q + kk * (2048 >> 4), idesc_acc, (qh | kk) != 0);
+                            }
+                        }
+                    }
+                    if ((qh & 1) || qh == NQH - 1) {
+                        // both halves of query tile qt are in shared memory: dQ_qt (+)= dS . K_kc over the nk keys
+                        const int qt = qh >> 1;
+                        const uint64_t a_ds = ddS_mn + (uint32_t)((tci & 1) * (32768 >> 4));
+                        const uint64_t b_k = dK_mn + (uint32_t)(kc * (16384 >> 4));
+                        const uint32_t dq = tmem_base + kColDQ + qt * 64;
+                        const int nkk2 = nk >> 4;
+                        if (leader) {
+#pragma unroll
+                            for (int kk = 0; kk < 8; ++kk)
+                                if (kk < nkk2)
+                                    umma_f16_ss(dq, a_ds + kk * (2048 >> 4), b_k + kk * (2048 >> 4), idesc_dq, (kc | kk) != 0);
+                        }
+                        ++tci;
+                    }
+                    if (leader) {
+                        if (qh == NQH - 1) umma_commit(acc_full);
+                        // load group 0 (tile / chunk 0) is last read by the steps of query tile 0 in the last key chunk
+                        if (kc == KC - 1 && qh == (NQH > 1 ? 1 : 0)) umma_commit(&g_free[0]);
+                        if (kc == KC - 1 && qh == NQH - 1 && QT > 1) umma_commit(&g_free[1]);
+                    }
+                    __syncwarp();
+                }
+            }
+        }
+    } else if (warp < 10) {
+        // ============================== row warps: softmax backward ==============================
+        const int quarter = warp & 3;        // TMEM lane quarter this warp may access
+        const int group = (warp - 2) >> 2;   // the two warps of a quarter split the query columns
+        const int r = quarter * 32 + lane;   // key inside the chunk
+        const uint32_t t_lane = tmem_base + (uint32_t(quarter * 32) << 16);
+        const int sw = r & 7;
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const float sl2 = p.scale_log2e;
+        uint32_t gi = 0, tci = 0;
+        int it = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
+            if (threadIdx.x == 64) FMHA_DBG(1, 10);
+            mbar_wait(d_full, (uint32_t)it & 1);  // D and lse of this unit are in shared memory
+            if (threadIdx.x == 64) FMHA_DBG(1, 12);
+            for (int kc = 0; kc < KC; ++kc) {
+                const int nk = (Lp - kc * 128) < 128 ? (Lp - kc * 128) : 128;
+                const bool live = quarter * 32 < nk;  // warp-uniform: some of this warp's keys exist
+                const int key = kc * 128 + r;
+                const bool key_ok = key < p.L;
+                const int warp_key_hi = kc * 128 + quarter * 32 + 31;
+                for (int qh = 0; qh < NQH; ++qh, ++gi) {
+                    const uint32_t b = gi & 1;
+                    const int nq = (Lp - qh * 64) < 64 ? (Lp - qh * 64) : 64;
+                    // query columns [0, 32) -> group 0, [32, 64) -> group 1
+                    const int cb = group * 32, ce = nq < cb + 32 ? nq : cb + 32;
+                    if (threadIdx.x == 64) FMHA_DBG(1, 13);
+                    mbar_wait(&st_full[b], (gi >> 1) & 1);
+                    tc_fence_after();
+                    if (threadIdx.x == 64) FMHA_DBG(1, 14);
+                    if (live) {
+                        const uint32_t tS = t_lane + b * 128, tDP = tS + 64;
+                        uint8_t* ds_row = sdS + (tci & 1) * 32768u + (uint32_t)(qh & 1) * 16384u + row_off;
+                        for (int c0 = cb; c0 < ce; c0 += 16) {
+                            uint32_t s[16], dp[16];
+                            tmem_ld_32x32b_x16(tS + c0, s);
+                            tmem_ld_32x32b_x16(tDP + c0, dp);
+                            const int q0 = qh * 64 + c0;
+                            float l2[16], Dq[16];
+#pragma unroll
+                            for (int v = 0; v < 4; ++v) {
+                                const float4 a = *reinterpret_cast<const float4*>(sL2 + q0 + 4 * v);
+                                const float4 c = *reinterpret_cast<const float4*>(sD + q0 + 4 * v);
+                                l2[4 * v] = a.x, l2[4 * v + 1] = a.y, l2[4 * v + 2] = a.z, l2[4 * v + 3] = a.w;
+                                Dq[4 * v] = c.x, Dq[4 * v + 1] = c.y, Dq[4 * v + 2] = c.z, Dq[4 * v + 3] = c.w;
+                            }
+                            tmem_ld_wait();
+                            float pv[16], dsv[16];
+                            // warp-uniform: every (key of this warp, query of this group) pair is inside the mask,
+                            // except for keys >= L, which are zeroed per thread afterwards
+                            if (q0 + 16 <= p.L && (!p.causal || warp_key_hi <= q0)) {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    pv[j] = ex2_approx(fmaf(__uint_as_float(s[j]), sl2, -l2[j]));
+                                    dsv[j] = pv[j] * (__uint_as_float(dp[j]) - Dq[j]);
+                                }
+                                if (!key_ok) {
+#pragma unroll
+                                    for (int j = 0; j < 16; ++j) pv[j] = 0.f, dsv[j] = 0.f;
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 16; ++j) {
+                                    const bool ok = key_ok && q0 + j < p.L && (!p.causal || key <= q0 + j);
+                                    pv[j] = ok ? ex2_approx(fmaf(__uint_as_float(s[j]), sl2, -l2[j])) : 0.f;
+                                    dsv[j] = ok ? pv[j] * (__uint_as_float(dp[j]) - Dq[j]) : 0.f;
+                                }
+                            }
+                            uint32_t pp[8], dd[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                pp[j] = pack_half2(pv[2 * j], pv[2 * j + 1]);
+                                dd[j] = pack_half2(dsv[2 * j], dsv[2 * j + 1]);
+                            }
+                            // fp16 columns of queries [c0, c0+16): 8 TMEM columns inside this warp's own part of the tile
+                            const uint32_t pc = (uint32_t)(c0 >> 1) + (c0 >= 32 ? 16u : 0u);
+                            tmem_st_32x32b_x8(tS + pc, pp);
+                            tmem_st_32x32b_x8(tDP + pc, dd);
+                            const int u = c0 >> 3;
+                            *reinterpret_cast<uint4*>(ds_row + ((u ^ sw) << 4)) = make_uint4(dd[0], dd[1], dd[2], dd[3]);
+                            *reinterpret_cast<uint4*>(ds_row + (((u + 1) ^ sw) << 4)) = make_uint4(dd[4], dd[5], dd[6], dd[7]);
+                        }
+                        tmem_st_wait();
+                    }
+                    fence_proxy_async_smem();
+                    tc_fence_before();
+                    mbar_arrive(&p_ready[b]);
+                    if (threadIdx.x == 64) FMHA_DBG(1, 15);
+                    if ((qh & 1) || qh == NQH - 1) ++tci;
                 }
             }
         }
     } else {
-        // ============================== row warps: softmax backward + epilogues ==============================
-        const int quarter = warp & 3;        // TMEM lane quarter this warp may access
-        const int group = (warp - 2) >> 2;   // the two warps of a quarter split the key columns / output columns
-        const int r = quarter * 32 + lane;
-        const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16);
-        const int etid = threadIdx.x - 64;
+        // ============================== epilogue warps ==============================
+        // Per unit: D = rowsum(dO o O) and lse*log2e of the NEXT unit (global loads, latency hidden behind this unit's
+        // steps, published once this unit's steps are over); dK / dV after each key chunk and dQ after the last one:
+        // TMEM -> fp16 -> swizzled staging tile -> TMA store.  The MMA warp waits for `acc_free` before it overwrites
+        // an accumulator these warps read.
+        const int quarter = warp & 3;
+        const int r = quarter * 32 + lane;  // row of an output tile == TMEM lane
+        const uint32_t t_lane = tmem_base + (uint32_t(quarter * 32) << 16);
+        const bool leader = threadIdx.x == 320;
         const int sw = r & 7;
         const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
-        uint32_t gi = 0, gacc = 0;
+        uint32_t gacc = 0;
 
-        // fp32 TMEM row, 32 columns [col + 32*group, ..) * mul -> fp16 -> units 4*group.. of row r of a swizzled
-        // [128 x 64] staging tile
-        auto stage_half = [&](uint32_t col, float mul, uint8_t* tile) {
-            uint32_t a[32];
-            tmem_ld_32x32(t_row + col + 32 * group, a);
-            tmem_ld_wait();
-            uint8_t* orow = tile + row_off;
+        // D and lse*log2e of row r of query tile qt of a unit (0 for rows >= L)
+        auto row_stats = [&](int unit, int qt, float& Dv, float& l2) {
+            const int h = unit % p.heads, n = unit / p.heads;
+            const int q = qt * 128 + r;
+            Dv = 0.f, l2 = 0.f;
+            if (q < p.L) {
+                const uint4* po = reinterpret_cast<const uint4*>(p.o + ((size_t)n * p.L + q) * d + h * 64);
+                const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)n * p.L + q) * d + h * 64);
+                float acc = 0.f;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const uint32_t* s = a + u * 8;
-                *reinterpret_cast<uint4*>(orow + (((u + 4 * group) ^ sw) << 4)) = make_uint4(
-                    pack_half2(__uint_as_float(s[0]) * mul, __uint_as_float(s[1]) * mul),
-                    pack_half2(__uint_as_float(s[2]) * mul, __uint_as_float(s[3]) * mul),
-                    pack_half2(__uint_as_float(s[4]) * mul, __uint_as_float(s[5]) * mul),
-                    pack_half2(__uint_as_float(s[6]) * mul, __uint_as_float(s[7]) * mul));
+                for (int i = 0; i < 8; ++i) {
+                    const uint4 a = __ldg(po + i), b = __ldg(pd + i);
+                    const __half2* ha = reinterpret_cast<const __half2*>(&a);
+                    const __half2* hb = reinterpret_cast<const __half2*>(&b);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
+                        acc = fmaf(fa.x, fb.x, acc);
+                        acc = fmaf(fa.y, fb.y, acc);
+                    }
+                }
+                Dv = acc;
+                l2 = p.lse[((size_t)n * p.heads + h) * p.L + q] * 1.4426950408889634f;
             }
         };
+        auto publish_stats = [&](const float (&Dv)[2], const float (&l2)[2]) {
+            for (int qt = 0; qt < QT; ++qt) {
+                sD[qt * 128 + r] = Dv[qt];
+                sL2[qt * 128 + r] = l2[qt];
+            }
+            mbar_arrive(d_full);
+        };
+        // 64 fp32 TMEM columns of row r, scaled -> 32 packed fp16 pairs
+        auto load_row = [&](uint32_t col, float mul, uint32_t (&pk)[32]) {
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {  // 32 columns at a time keeps the register peak low
+                uint32_t a[32];
+                tmem_ld_32x32(t_lane + col + 32 * hh, a);
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 16; ++j)
+                    pk[16 * hh + j] = pack_half2(__uint_as_float(a[2 * j]) * mul, __uint_as_float(a[2 * j + 1]) * mul);
+            }
+        };
+        auto stage_row = [&](const uint32_t (&pk)[32], uint8_t* tile) {
+            uint8_t* orow = tile + row_off;
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                *reinterpret_cast<uint4*>(orow + ((u ^ sw) << 4)) = make_uint4(pk[4 * u], pk[4 * u + 1], pk[4 * u + 2], pk[4 * u + 3]);
+        };
 
+        float Dn[2] = {0.f, 0.f}, Ln[2] = {0.f, 0.f};
+        if ((int)blockIdx.x < p.num_units) {
+            for (int qt = 0; qt < QT; ++qt) row_stats(blockIdx.x, qt, Dn[qt], Ln[qt]);
+            publish_stats(Dn, Ln);
+        }
         for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
             const int h = unit % p.heads, n = unit / p.heads;
-            // D = rowsum(dO o O) and lse*log2e: warp group g computes the rows of query tile g, shared through smem
-            if (group < QT) {
-                const int q = group * 128 + r;
-                float acc = 0.f, l2 = 0.f;
-                if (q < p.L) {
-                    const uint4* po = reinterpret_cast<const uint4*>(p.o + ((size_t)n * p.L + q) * d + h * 64);
-                    const uint4* pd = reinterpret_cast<const uint4*>(p.d_o + ((size_t)n * p.L + q) * d + h * 64);
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const uint4 a = __ldg(po + i), b = __ldg(pd + i);
-                        const __half2* ha = reinterpret_cast<const __half2*>(&a);
-                        const __half2* hb = reinterpret_cast<const __half2*>(&b);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const float2 fa = __half22float2(ha[j]), fb = __half22float2(hb[j]);
-                            acc = fmaf(fa.x, fb.x, acc);
-                            acc = fmaf(fa.y, fb.y, acc);
-                        }
-                    }
-                    l2 = p.lse[((size_t)n * p.heads + h) * p.L + q] * 1.4426950408889634f;
-                }
-                sD[q] = acc;
-                sL2[q] = l2;
-            }
-            named_bar_sync(1, kFmhaBwdRowThreads);
-            float Dv[2], lse2[2];
-            Dv[0] = sD[r];
-            lse2[0] = sL2[r];
-            Dv[1] = QT > 1 ? sD[128 + r] : 0.f;
-            lse2[1] = QT > 1 ? sL2[128 + r] : 0.f;
-
+            const int next = unit + gridDim.x;
+            if (next < p.num_units)
+                for (int qt = 0; qt < QT; ++qt) row_stats(next, qt, Dn[qt], Ln[qt]);
             for (int kc = 0; kc < KC; ++kc) {
-                const int nk = (Lp - kc * 128) < 128 ? (Lp - kc * 128) : 128;
-                const int half0 = ((nk >> 4) + 1) / 2 * 16;  // columns [0, half0) -> group 0, [half0, nk) -> group 1
-                const int cb = group ? half0 : 0, ce = group ? nk : half0;
-                for (int qt = 0; qt < QT; ++qt) {
-                    const int q = qt * 128 + r;
-                    const bool qok = q < p.L;
-                    int kmax = p.causal ? (q + 1 < p.L ? q + 1 : p.L) : p.L;  // valid keys: [0, kmax)
-                    if (!qok) kmax = 0;
-                    const float Dq = Dv[qt], l2 = lse2[qt];
-                    mbar_wait(s_full, gi & 1);
-                    ++gi;
-                    tc_fence_after();
-                    for (int c0 = cb; c0 < ce; c0 += 16) {
-                        uint32_t s[16], dp[16];
-                        tmem_ld_32x32b_x16(t_row + kColS + c0, s);
-                        tmem_ld_32x32b_x16(t_row + kColDP + c0, dp);
-                        tmem_ld_wait();
-                        float pv[16], dsv[16];
-                        const int key0 = kc * 128 + c0;
-                        if (key0 + 16 <= kmax) {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                pv[j] = ex2_approx(fmaf(__uint_as_float(s[j]), p.scale_log2e, -l2));
-                                dsv[j] = pv[j] * (__uint_as_float(dp[j]) - Dq);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < 16; ++j) {
-                                const bool ok = key0 + j < kmax;
-                                pv[j] = ok ? ex2_approx(fmaf(__uint_as_float(s[j]), p.scale_log2e, -l2)) : 0.f;
-                                dsv[j] = ok ? pv[j] * (__uint_as_float(dp[j]) - Dq) : 0.f;
-                            }
-                        }
-                        const uint32_t off = (uint32_t)(c0 >> 6) * 16384u + row_off;
-                        const int u = (c0 & 63) >> 3;
-                        *reinterpret_cast<uint4*>(sP + off + ((u ^ sw) << 4)) = make_uint4(
-                            pack_half2(pv[0], pv[1]), pack_half2(pv[2], pv[3]), pack_half2(pv[4], pv[5]), pack_half2(pv[6], pv[7]));
-                        *reinterpret_cast<uint4*>(sP + off + (((u + 1) ^ sw) << 4)) = make_uint4(
-                            pack_half2(pv[8], pv[9]), pack_half2(pv[10], pv[11]), pack_half2(pv[12], pv[13]),
-                            pack_half2(pv[14], pv[15]));
-                        *reinterpret_cast<uint4*>(sdS + off + ((u ^ sw) << 4)) = make_uint4(
-                            pack_half2(dsv[0], dsv[1]), pack_half2(dsv[2], dsv[3]), pack_half2(dsv[4], dsv[5]),
-                            pack_half2(dsv[6], dsv[7]));
-                        *reinterpret_cast<uint4*>(sdS + off + (((u + 1) ^ sw) << 4)) = make_uint4(
-                            pack_half2(dsv[8], dsv[9]), pack_half2(dsv[10], dsv[11]), pack_half2(dsv[12], dsv[13]),
-                            pack_half2(dsv[14], dsv[15]));
-                    }
-                    fence_proxy_async_smem();
+                mbar_wait(acc_full, gacc & 1);  // dK_kc, dV_kc (and, for the last chunk, dQ) complete: lanes = rows
+                ++gacc;
+                tc_fence_after();
+                if (leader) FMHA_DBG(1, 16);
+                uint32_t pk[32];
+                if (leader) tma_store_wait_read<0>();  // the previous stores have left the staging tiles
+                named_bar_sync(2, 128);
+                load_row(kColDK, 0.125f, pk);
+                stage_row(pk, sSt);
+                load_row(kColDV, 1.0f, pk);
+                stage_row(pk, sSt + 16384);
+                if (kc < KC - 1) {
                     tc_fence_before();
-                    mbar_arrive(p_ready);
-
-                    if (qt == QT - 1) {
-                        // dK_kc, dV_kc are complete: lanes = keys kc*128 + r
-                        mbar_wait(acc_full, gacc & 1);
-                        ++gacc;
-                        tc_fence_after();
-                        if (etid == 0) tma_store_wait_read<0>();
-                        named_bar_sync(1, kFmhaBwdRowThreads);
-                        stage_half(kColDK, 0.125f, sSt);
-                        stage_half(kColDV, 1.0f, sSt + 16384);
-                        fence_proxy_async_smem();
-                        named_bar_sync(1, kFmhaBwdRowThreads);
-                        if (etid == 0) {
-                            tma_store_3d(&tmap_dqkv, sSt, d + h * 64, kc * 128, n);
-                            tma_store_3d(&tmap_dqkv, sSt + 16384, 2 * d + h * 64, kc * 128, n);
-                            tma_store_commit();
-                        }
+                    mbar_arrive(acc_free);
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (leader) {
+                        tma_store_3d(&tmap_dqkv, sSt, d + h * 64, kc * 128, n);
+                        tma_store_3d(&tmap_dqkv, sSt + 16384, 2 * d + h * 64, kc * 128, n);
+                        tma_store_commit();
+                        FMHA_DBG(1, 17);
+                    }
+                } else {
+                    // last chunk: the steps of this unit are over -> dQ is complete and the row warps are done with
+                    // the per-query statistics
+                    uint32_t pq[32];
+                    load_row(kColDQ, 0.125f, pk);
+                    if (QT > 1) load_row(kColDQ + 64, 0.125f, pq);
+                    tc_fence_before();
+                    mbar_arrive(acc_free);
+                    if (next < p.num_units) publish_stats(Dn, Ln);
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (leader) {
+                        tma_store_3d(&tmap_dqkv, sSt, d + h * 64, kc * 128, n);
+                        tma_store_3d(&tmap_dqkv, sSt + 16384, 2 * d + h * 64, kc * 128, n);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();
+                    }
+                    named_bar_sync(2, 128);
+                    stage_row(pk, sSt);
+                    if (QT > 1) stage_row(pq, sSt + 16384);
+                    fence_proxy_async_smem();
+                    named_bar_sync(2, 128);
+                    if (leader) {
+                        for (int qt = 0; qt < QT; ++qt) tma_store_3d(&tmap_dqkv, sSt + qt * 16384, h * 64, qt * 128, n);
+                        tma_store_commit();
+                        FMHA_DBG(1, 18);
                     }
                 }
-            }
-            // dQ tiles (the last acc_full covered every MMA of the unit)
-            if (etid == 0) tma_store_wait_read<0>();
-            named_bar_sync(1, kFmhaBwdRowThreads);
-            for (int qt = 0; qt < QT; ++qt) stage_half(kColDQ + qt * 64, 0.125f, sSt + qt * 16384);
-            tc_fence_before();
-            fence_proxy_async_smem();
-            named_bar_sync(1, kFmhaBwdRowThreads);
-            if (etid == 0) {
-                for (int qt = 0; qt < QT; ++qt) tma_store_3d(&tmap_dqkv, sSt + qt * 16384, h * 64, qt * 128, n);
-                tma_store_commit();
             }
         }
-        if (etid == 0) tma_store_wait_all();
+        if (leader) tma_store_wait_all();
     }
 
     tc_fence_before();
@@ -332,17 +478,13 @@ inline bool fmha_bwd_sm100_supported(int L) { return L >= 1 && L <= 256; }
 inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const void* lse, void* dqkv, int N, int L,
                           int d, int heads, int causal, cudaStream_t stream) {
     const int Lp = (L + 15) / 16 * 16;
-    const int KC = (Lp + 127) / 128;
-    const int box_h = KC == 1 ? Lp : 128;  // rows of one K / V chunk (chunk 1 may run past L: zero-filled)
-    CUtensorMap tq, tkv, tdo, tdq;
+    CUtensorMap tq, tdo, tdq;
     {
+        // one map serves Q, K and V (different column offsets): boxes of 128 rows, rows >= L zero-filled
         uint64_t dims[3] = {(uint64_t)3 * d, (uint64_t)L, (uint64_t)N};
         uint64_t str[2] = {(uint64_t)3 * d * 2, (uint64_t)L * 3 * d * 2};
         uint32_t box_q[3] = {64u, 128u, 1u};
-        uint32_t box_kv[3] = {64u, (uint32_t)box_h, 1u};
         int rc = make_tmap_f16(&tq, qkv, 3, dims, str, box_q);
-        if (rc) return rc;
-        rc = make_tmap_f16(&tkv, qkv, 3, dims, str, box_kv);
         if (rc) return rc;
         rc = make_tmap_f16(&tdq, dqkv, 3, dims, str, box_q);
         if (rc) return rc;
@@ -360,10 +502,10 @@ inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const
     p.heads = heads;
     p.d = d;
     p.QT = (L + 127) / 128;
-    p.KC = KC;
+    p.KC = (Lp + 127) / 128;
+    p.NQH = (Lp + 63) / 64;
     p.causal = causal;
     p.num_units = N * heads;
-    p.box_h = box_h;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     p.lse = static_cast<const float*>(lse);
     p.o = static_cast<const __half*>(o);
@@ -371,11 +513,9 @@ inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const
     if (p.QT != p.KC) return fail(MVLPT_ESHAPE, "fmha_bwd_sm100: internal: QT != KC for L=%d", L);
     p.off_do = (uint32_t)p.QT * 16384u;
     p.off_k = 2u * p.off_do;
-    const uint32_t kv = (uint32_t)((KC * box_h * 128 + 1023) / 1024 * 1024);
-    p.off_v = p.off_k + kv;
-    p.off_p = p.off_v + kv;
-    p.off_ds = p.off_p + 32768u;
-    p.off_stage = p.off_ds + 32768u;
+    p.off_v = p.off_k + (uint32_t)p.KC * 16384u;
+    p.off_ds = p.off_v + (uint32_t)p.KC * 16384u;
+    p.off_stage = p.off_ds + 65536u;
     p.off_row = p.off_stage + 32768u;
     p.off_bar = p.off_row + 2048u;
     const size_t smem = (size_t)p.off_bar + 128;
@@ -386,7 +526,7 @@ inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const
         attr = smem;
     }
     const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-    fmha_bwd_tc_kernel<<<grid, kFmhaBwdThreads, smem, stream>>>(tq, tkv, tdo, tdq, p);
+    fmha_bwd_tc_kernel<<<grid, kFmhaBwdThreads, smem, stream>>>(tq, tq, tdo, tdq, p);
     return launched("fmha_bwd_tc");
 }
 

@@ -363,43 +363,56 @@ fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
         }
     } else if (warp == 1) {
         // ============================== MMA issuer ==============================
-        if (lane == 0) {
-            const uint32_t idesc_s = umma_idesc_f16(128, (uint32_t)Lp, 0, 0);
-            const uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);  // B (V) is MN-major
-            const uint32_t idesc_sum = umma_idesc_f16(128, 16, 0, 0);
-            const uint64_t ones_desc = umma_desc_k_sw128(smem_u32(sOnes));
-            auto issue_s = [&](int t) {
-                const int u = t / QT, qt = t - u * QT, s = u & 1, b = t & 1;
-                uint8_t* st = smem + s * p.stage_bytes;
-                if (qt == 0) mbar_wait(&qk_full[s], (uint32_t)(u >> 1) & 1);
-                if (t >= 2) mbar_wait(&o_read[b], (uint32_t)((t >> 1) - 1) & 1);  // O of tile t-2 left the buffer
-                tc_fence_after();
-                const uint64_t q_desc = umma_desc_k_sw128(smem_u32(st + qt * 16384));
-                const uint64_t k_desc = umma_desc_k_sw128(smem_u32(st + p.off_k));
+        // The whole warp runs the control flow (warp-uniform operands stay in uniform registers); one elected lane
+        // issues the MMAs and commits.
+        const bool leader = elect_one();
+        const uint32_t idesc_s = umma_idesc_f16(128, (uint32_t)Lp, 0, 0);
+        const uint32_t idesc_pv = umma_idesc_f16(128, 64, 0, 1);  // B (V) is MN-major
+        const uint32_t idesc_sum = umma_idesc_f16(128, 16, 0, 0);
+        const uint64_t ones_desc = umma_desc_k_sw128(smem_u32(sOnes));
+        const uint64_t stage_k0 = umma_desc_k_sw128(smem_u32(smem));  // stage s: + s * (stage_bytes >> 4)
+        const uint64_t stage_v0 = umma_desc_mn_sw128(smem_u32(smem + p.off_v), 1024);
+        const int ksteps = Lp / 16, ks0 = p.csplit / 16;  // steps [0, ks0) read P of half 0, the rest P of half 1
+        auto issue_s = [&](int t) {
+            const int u = t / QT, qt = t - u * QT, s = u & 1, b = t & 1;
+            if (qt == 0) mbar_wait(&qk_full[s], (uint32_t)(u >> 1) & 1);
+            if (t >= 2) mbar_wait(&o_read[b], (uint32_t)((t >> 1) - 1) & 1);  // O of tile t-2 left the buffer
+            tc_fence_after();
+            const uint64_t st_desc = stage_k0 + (uint32_t)s * (p.stage_bytes >> 4);
+            const uint64_t q_desc = st_desc + (uint32_t)(qt * (16384 >> 4));
+            const uint64_t k_desc = st_desc + (p.off_k >> 4);
+            if (leader) {
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     umma_f16_ss(tmem_base + b * 256, q_desc + 2 * k, k_desc + 2 * k, idesc_s, k != 0);
                 umma_commit(&s_full[b]);
-            };
-            if (T > 0) issue_s(0);
-            for (int t = 0; t < T; ++t) {
-                if (t + 1 < T) issue_s(t + 1);
-                const int u = t / QT, qt = t - u * QT, s = u & 1, b = t & 1;
-                const uint32_t sV = smem_u32(smem + s * p.stage_bytes + p.off_v);
-                mbar_wait(&p_full[b], (uint32_t)(t >> 1) & 1);
-                if (qt == 0) mbar_wait(&v_full[s], (uint32_t)(u >> 1) & 1);
-                tc_fence_after();
-                const uint32_t tb = tmem_base + b * 256;
-                const int ksteps = Lp / 16;
-                for (int kk = 0; kk < ksteps; ++kk) {
-                    const int k0 = kk * 16;  // first key of this step -> where its P columns live
-                    const uint32_t pa = tb + (k0 < p.csplit ? (k0 >> 1) : p.csplit + ((k0 - p.csplit) >> 1));
-                    umma_f16_ts(tb + p.o_col, pa, umma_desc_mn_sw128(sV + kk * 2048, 1024), idesc_pv, kk != 0);
-                    umma_f16_ts(tb + p.sum_col, pa, ones_desc, idesc_sum, kk != 0);
+            }
+            __syncwarp();
+        };
+        if (T > 0) issue_s(0);
+        for (int t = 0; t < T; ++t) {
+            if (t + 1 < T) issue_s(t + 1);
+            const int u = t / QT, qt = t - u * QT, s = u & 1, b = t & 1;
+            mbar_wait(&p_full[b], (uint32_t)(t >> 1) & 1);
+            if (qt == 0) mbar_wait(&v_full[s], (uint32_t)(u >> 1) & 1);
+            tc_fence_after();
+            const uint32_t tb = tmem_base + b * 256;
+            const uint32_t o_acc = tb + p.o_col, sum_acc = tb + p.sum_col;
+            const uint32_t pa1 = tb + p.csplit - (p.csplit >> 1);  // + 8 kk = P columns of step kk >= ks0
+            const uint64_t v_desc = stage_v0 + (uint32_t)s * (p.stage_bytes >> 4);
+            if (leader) {
+                for (int kk = 0; kk < ks0; ++kk) {
+                    umma_f16_ts(o_acc, tb + kk * 8, v_desc + kk * (2048 >> 4), idesc_pv, kk != 0);
+                    umma_f16_ts(sum_acc, tb + kk * 8, ones_desc, idesc_sum, kk != 0);
+                }
+                for (int kk = ks0; kk < ksteps; ++kk) {
+                    umma_f16_ts(o_acc, pa1 + kk * 8, v_desc + kk * (2048 >> 4), idesc_pv, 1);
+                    umma_f16_ts(sum_acc, pa1 + kk * 8, ones_desc, idesc_sum, 1);
                 }
                 umma_commit(&o_full[b]);
                 if (qt == QT - 1) umma_commit(&stage_free[s]);
             }
+            __syncwarp();
         }
     } else {
         // ============================== softmax + epilogue: group g owns TMEM buffer g ==============================
