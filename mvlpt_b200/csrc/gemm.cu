@@ -83,6 +83,96 @@ static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, c
     return launched("gemm_f16_tn");
 }
 
+// CTA-pair kernel (256 x 256 tile per cluster of two CTAs): N a multiple of 256, at least one full 256-row tile.
+static bool use_2sm(const mvlpt_gemm_desc* d) {
+    static int off = -1;
+    if (off < 0) off = getenv("MVLPT_GEMM_1SM") ? 1 : 0;
+    return !off && d->N >= 256 && (d->N % 256) == 0 && d->M >= 256;
+}
+
+template <bool F32>
+static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* in, void* aux_out, void* out,
+                           GemmEpilogue ep, cudaStream_t stream) {
+    constexpr int kStage = 32768;
+    // operand-ring depth / output-ring slots out of the 227 KB: deep operand ring for plain epilogues, deep slab ring
+    // when the epilogue has a TMA-loaded input or a second output
+    const int per = ep.has_aux_out ? 2 : 1;
+    int stages = (ep.has_in || ep.has_aux_out) ? 4 : 6;
+    static int forced = -1;
+    if (forced < 0) {
+        const char* e = getenv("MVLPT_GEMM2_STAGES");
+        forced = e ? atoi(e) : 0;
+    }
+    if (forced >= 2 && forced <= kGemmMaxStages2) stages = forced;
+    int slabs = (kGemmSmemBudget + 1024 - stages * kStage) / kGemmSlab;
+    int ring = slabs / per;
+    if (ring > kGemmMaxRing) ring = kGemmMaxRing;
+    if (ring < 2) return fail(MVLPT_ESHAPE, "mvlpt_gemm: no room for the output ring");
+    ep.stages = stages;
+    ep.ring = ring;
+    const int smem_bytes = stages * kStage + ring * per * kGemmSlab + 256;
+    CUtensorMap ta, tw, to, tx, ti;
+    {
+        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
+        uint64_t str[1] = {(uint64_t)d->lda * 2};
+        uint32_t box[2] = {(uint32_t)kGemmBK, (uint32_t)kGemmBM};
+        int rc = make_tmap_f16(&ta, A, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->N};
+        uint64_t str[1] = {(uint64_t)d->ldw * 2};
+        uint32_t box[2] = {(uint32_t)kGemmBK, 128u};  // each CTA of the pair stages half of the 256 W rows
+        int rc = make_tmap_f16(&tw, W, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+        uint64_t str[1] = {(uint64_t)d->ld_out * (F32 ? 4 : 2)};
+        uint32_t box[2] = {F32 ? 32u : 64u, (uint32_t)kGemmBM};
+        int rc = make_tmap(&to, out, F32 ? 1 : 0, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    tx = to;
+    ti = to;
+    if (in) {
+        uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+        uint64_t str[1] = {F32 ? (uint64_t)d->ld_out * 4 : (uint64_t)d->ld_aux * 2};
+        uint32_t box[2] = {F32 ? 32u : 64u, (uint32_t)kGemmBM};
+        int rc = make_tmap(&ti, in, F32 ? 1 : 0, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    if (aux_out) {
+        uint64_t dims[2] = {(uint64_t)d->N, (uint64_t)d->M};
+        uint64_t str[1] = {(uint64_t)d->ld_aux * 2};
+        uint32_t box[2] = {64u, (uint32_t)kGemmBM};
+        int rc = make_tmap_f16(&tx, aux_out, 2, dims, str, box);
+        if (rc) return rc;
+    }
+    static int attr = 0;
+    if (smem_bytes > attr) {
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(gemm_f16_tn_2sm_kernel<F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           smem_bytes));
+        attr = smem_bytes;
+    }
+    const int tiles = cdiv(d->M, 2 * kGemmBM) * cdiv(d->N, 256);
+    const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kGemm2Threads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    MVLPT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_f16_tn_2sm_kernel<F32>, ta, tw, to, tx, ti, d->M, d->N, d->K, ep));
+    return launched("gemm_f16_tn_2sm");
+}
+
 extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias,
                           const void* aux_in, void* aux_out, const void* resid, void* out, mvlpt_stream_t stream) {
     if (!d || !A || !W || !out) return fail(MVLPT_EINVAL, "mvlpt_gemm: null argument");
@@ -116,6 +206,9 @@ extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W
     ep.alpha = d->alpha;
     ep.stages = ep.ring = 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (use_2sm(d))
+        return d->out_f32 ? launch_gemm_2sm<true>(d, A, W, in, aux_out, out, ep, s)
+                          : launch_gemm_2sm<false>(d, A, W, in, aux_out, out, ep, s);
     if (d->N <= 128)
         return d->out_f32 ? launch_gemm<128, true>(d, A, W, in, aux_out, out, ep, s)
                           : launch_gemm<128, false>(d, A, W, in, aux_out, out, ep, s);

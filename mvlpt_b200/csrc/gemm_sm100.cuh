@@ -42,8 +42,10 @@ struct GemmEpilogue {
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
 constexpr int kGemmThreads = 192;
+constexpr int kGemm2Threads = 320;  // CTA-pair kernel: TMA warp, MMA warp, 8 epilogue warps
 constexpr int kGemmSlab = 16384;  // 128 rows x 128 bytes
 constexpr int kGemmMaxStages = 6;
+constexpr int kGemmMaxStages2 = 7;  // CTA-pair kernel: 32 KB stages
 constexpr int kGemmMaxRing = 6;
 constexpr int kGemmSmemBudget = 227 * 1024 - 1024 /*align slack*/ - 256 /*barriers*/;
 
@@ -73,6 +75,7 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ void gemm_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void gemm_bar_sync256() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read_n(int n) {
     switch (n) {
         case 0: tma_store_wait_read<0>(); break;
@@ -341,6 +344,300 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     if (warp == 1) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// CTA-pair variant (cta_group::2): a cluster of two CTAs on one TPC computes a 256 x 256 output tile with ONE
+// tcgen05.mma of M = 256 per K step.  Each CTA stages only its 128 rows of A and its 128 of the 256 W rows (N columns)
+// per stage — 32 KB instead of 48 KB — and the tensor cores of both SMs read the two W halves from both shared
+// memories, so the shared-memory traffic per SM (TMA fill + operand reads) drops from 192 to 128 bytes per clock, which
+// is what bounded the single-CTA kernel above (ncu: tensor pipe 85 % active at 60 % of its rate).
+// The even CTA issues the MMAs; TMA loads of both CTAs count on its `full` barrier; tcgen05.commit multicasts to the
+// `empty` / `tfull` barriers of both; the epilogue warps of both CTAs arrive on its `tempty` barrier.
+// The epilogue is the one of the kernel above, per CTA on its own 128 accumulator rows, with twice the warps.
+template <bool OUT_F32>
+__global__ void __launch_bounds__(kGemm2Threads, 1)
+gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
+                       const __grid_constant__ CUtensorMap tmap_out, const __grid_constant__ CUtensorMap tmap_aux,
+                       const __grid_constant__ CUtensorMap tmap_in, int M, int N, int K, GemmEpilogue ep) {
+    constexpr int BN = 256;
+    constexpr int kABytes = kGemmBM * kGemmBK * 2;       // this CTA's 128 rows of A
+    constexpr int kBBytes = (BN / 2) * kGemmBK * 2;      // this CTA's 128 rows of W
+    constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr int SW = OUT_F32 ? 32 : 64;  // output columns per 128-byte slab row
+    constexpr int kSteps = BN / SW;
+    const int kStages = ep.stages;
+    const int per = ep.has_aux_out ? 2 : 1;  // slabs per ring slot
+    extern __shared__ __align__(1024) uint8_t smem_gemm2[];
+    uint8_t* smem = smem_gemm2;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + kStages * kABytes;
+    uint8_t* smem_e = smem + kStages * kStageBytes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_e + ep.ring * per * kGemmSlab);
+    uint64_t* full_bar = bars;                          // used in the even CTA only
+    uint64_t* empty_bar = bars + kGemmMaxStages2;
+    uint64_t* tfull_bar = bars + 2 * kGemmMaxStages2;
+    uint64_t* tempty_bar = tfull_bar + 2;               // used in the even CTA only
+    uint64_t* in_full = tempty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(in_full + kGemmMaxRing);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const int m_tiles = (M + 2 * kGemmBM - 1) / (2 * kGemmBM);
+    const int n_tiles = (N + BN - 1) / BN;
+    const int num_tiles = m_tiles * n_tiles;
+    const int k_blocks = (K + kGemmBK - 1) / kGemmBK;
+
+    if (warp == 0 && lane == 0) {
+        if (smem_u32(smem) & 1023u) {
+            printf("mvlpt: gemm dynamic shared memory is not 1024-byte aligned\n");
+            __trap();
+        }
+        tma_prefetch_desc(&tmap_a);
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_out);
+        if (ep.has_aux_out) tma_prefetch_desc(&tmap_aux);
+        if (ep.has_in) tma_prefetch_desc(&tmap_in);
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], 1);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&tfull_bar[s], 1);
+            mbar_init(&tempty_bar[s], 16);  // 8 epilogue warps of each CTA
+        }
+        for (int s = 0; s < kGemmMaxRing; ++s) mbar_init(&in_full[s], 1);
+        mbar_fence_init();
+    }
+    if (warp == 1) {
+        tmem_alloc_2sm(tmem_slot, 512);
+        tmem_relinquish_2sm();
+    }
+    tc_fence_before();
+    cluster_sync_all();  // barriers of both CTAs are initialised before either touches the other's
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs) =====================
+        if (lane == 0) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM;
+                const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);  // both CTAs' bytes
+                    tma_load_2d_2sm(smem_a + stage * kABytes, &tmap_a, &full_bar[stage], kb * kGemmBK, m0);
+                    tma_load_2d_2sm(smem_b + stage * kBBytes, &tmap_w, &full_bar[stage], kb * kGemmBK, n0);
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (even CTA; the whole warp runs the loop, one lane issues) =====================
+        if (rank == 0) {
+            const bool leader = elect_one();
+            constexpr uint32_t idesc = umma_idesc_f16(2 * kGemmBM, BN, 0, 0);
+            const uint64_t a_base = umma_desc_k_sw128(smem_u32(smem_a));
+            const uint64_t b_base = umma_desc_k_sw128(smem_u32(smem_b));
+            int stage = 0;
+            uint32_t phase = 0;
+            int acc = 0;
+            uint32_t acc_phase = 0;
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kb = 0; kb < k_blocks; ++kb) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    const uint64_t a_desc = a_base + (uint32_t)(stage * (kABytes >> 4));
+                    const uint64_t b_desc = b_base + (uint32_t)(stage * (kBBytes >> 4));
+                    if (leader) {
+#pragma unroll
+                        for (int k = 0; k < kGemmBK / 16; ++k)
+                            umma_f16_ss_2sm(d_tmem, a_desc + 2 * k, b_desc + 2 * k, idesc, (kb | k) != 0);
+                        umma_commit_2sm(&empty_bar[stage]);
+                    }
+                    __syncwarp();
+                    if (++stage == kStages) { stage = 0; phase ^= 1; }
+                }
+                if (leader) umma_commit_2sm(&tfull_bar[acc]);
+                __syncwarp();
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            }
+        }
+    } else {
+        // ===================== epilogue (8 warps = 2 per TMEM lane quarter) =====================
+        // A thread owns one accumulator row; the two warps of a quarter split the columns of every 128-byte slab step
+        // (fp16: 32 + 32 of 64 columns, fp32: 16 + 16 of 32), so every scheduler has two epilogue warps to interleave.
+        constexpr int HC = SW / 2;             // accumulator columns per thread per step
+        const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;      // which half of the step's columns
+        const int r = quarter * 32 + lane;
+        const bool issuer = (threadIdx.x == 64);
+        const int sw = r & 7;
+        const uint32_t row_off = (uint32_t)(r >> 3) * 1024u + (uint32_t)(r & 7) * 128u;
+        const bool has_in = ep.has_in != 0;
+        const bool two = ep.has_aux_out != 0;
+        const bool scaled = ep.alpha != 1.f;
+        const int R = ep.ring;
+        int acc = 0;
+        uint32_t acc_phase = 0;
+        int g = 0;  // steps done by this CTA
+        const int my_tiles = pair < num_tiles ? (num_tiles - 1 - pair) / num_pairs + 1 : 0;
+        const int total_steps = my_tiles * kSteps;
+        // TMA load of the epilogue input of step gg into its ring slot (issuer thread only)
+        auto issue_in = [&](int gg) {
+            if (gg >= total_steps) return;
+            const int t = pair + (gg / kSteps) * num_pairs;
+            const int mm = (t / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM, nn = (t % n_tiles) * BN + (gg % kSteps) * SW;
+            const int slot = gg % R;
+            mbar_arrive_expect_tx(&in_full[slot], kGemmSlab);
+            tma_load_2d(smem_e + slot * kGemmSlab, &tmap_in, &in_full[slot], nn, mm);
+        };
+        if (has_in && issuer)
+            for (int gg = 0; gg < R - 1; ++gg) issue_in(gg);
+
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int m0 = (tile / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM;
+            const int n0 = (tile % n_tiles) * BN;
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * HC;
+#pragma unroll 1
+            for (int s = 0; s < kSteps; ++s, ++g) {
+                const int col0 = n0 + s * SW;
+                const int c0 = col0 + half * HC;  // first output column of this thread in this step
+                const int slot = g % R;
+                uint8_t* slab = smem_e + slot * per * kGemmSlab;
+                // bias of this thread's columns: issued first, its latency hides behind the waits below
+                uint4 braw[HC / 8];
+                const bool bias_vec = ep.bias != nullptr && c0 + HC <= N;
+                if (bias_vec) {
+#pragma unroll
+                    for (int q = 0; q < HC / 8; ++q) braw[q] = __ldg(reinterpret_cast<const uint4*>(ep.bias + c0) + q);
+                }
+                if (has_in) {
+                    mbar_wait(&in_full[slot], (uint32_t)(g / R) & 1);  // input landed (implies the slot was drained)
+                } else {
+                    // the slot about to be overwritten must have been drained by the TMA store of step g - R
+                    if (issuer) tma_store_wait_read_n(R - 1);
+                    gemm_bar_sync256();
+                }
+                uint8_t* orow = slab + row_off;
+                uint32_t raw[HC];
+                if constexpr (HC == 32) tmem_ld_32x32(t_row + s * SW, raw);
+                else tmem_ld_32x32b_x16(t_row + s * SW, raw);
+                tmem_ld_wait();
+                if (s == kSteps - 1) {
+                    // last TMEM read of this tile: hand the accumulator back to the MMA warp of the even CTA
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cta0(&tempty_bar[acc]);
+                }
+                float v[HC];
+#pragma unroll
+                for (int j = 0; j < HC; ++j) v[j] = __uint_as_float(raw[j]);
+                if (scaled) {
+#pragma unroll
+                    for (int j = 0; j < HC; ++j) v[j] *= ep.alpha;
+                }
+                if (bias_vec) {
+#pragma unroll
+                    for (int q = 0; q < HC / 8; ++q) {
+                        const __half2* h2 = reinterpret_cast<const __half2*>(&braw[q]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __half22float2(h2[j]);
+                            v[q * 8 + 2 * j] += f.x;
+                            v[q * 8 + 2 * j + 1] += f.y;
+                        }
+                    }
+                } else if (ep.bias) {
+#pragma unroll
+                    for (int j = 0; j < HC; ++j)
+                        if (c0 + j < N) v[j] += __half2float(ep.bias[c0 + j]);
+                }
+                if constexpr (OUT_F32) {
+                    // fp32 slab row = 32 columns = 8 units of 4; this thread fills units 4*half .. 4*half+3; the
+                    // residual is already in the slab
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        uint4* dst = reinterpret_cast<uint4*>(orow + (((4 * half + u) ^ sw) << 4));
+                        if (has_in) {
+                            const uint4 x = *dst;
+                            v[4 * u + 0] += __uint_as_float(x.x);
+                            v[4 * u + 1] += __uint_as_float(x.y);
+                            v[4 * u + 2] += __uint_as_float(x.z);
+                            v[4 * u + 3] += __uint_as_float(x.w);
+                        }
+                        *dst = make_uint4(__float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
+                                          __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
+                    }
+                } else {
+                    // fp16 slab row = 64 columns = 8 units of 8; this thread fills units 4*half .. 4*half+3
+                    if (ep.act == ACT_QUICKGELU) {
+                        if (two) {
+                            uint8_t* arow = orow + kGemmSlab;
+#pragma unroll
+                            for (int u = 0; u < 4; ++u)
+                                *reinterpret_cast<uint4*>(arow + (((4 * half + u) ^ sw) << 4)) =
+                                    make_uint4(pack_h2(v[8 * u], v[8 * u + 1]), pack_h2(v[8 * u + 2], v[8 * u + 3]),
+                                               pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7]));
+                        }
+#pragma unroll
+                        for (int j = 0; j < HC; ++j) v[j] = quickgelu_f(v[j]);
+                    } else if (ep.act == ACT_MUL_DQUICKGELU) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) {
+                            const uint4 t4 = *reinterpret_cast<const uint4*>(orow + (((4 * half + u) ^ sw) << 4));
+                            const __half2* h2 = reinterpret_cast<const __half2*>(&t4);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const float2 f = __half22float2(h2[j]);
+                                v[8 * u + 2 * j] *= dquickgelu_f(f.x);
+                                v[8 * u + 2 * j + 1] *= dquickgelu_f(f.y);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < HC / 8; ++u)
+                        *reinterpret_cast<uint4*>(orow + (((4 * half + u) ^ sw) << 4)) =
+                            make_uint4(pack_h2(v[8 * u], v[8 * u + 1]), pack_h2(v[8 * u + 2], v[8 * u + 3]),
+                                       pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7]));
+                }
+                fence_proxy_async_smem();
+                gemm_bar_sync256();
+                if (issuer) {
+                    if (col0 < N) {
+                        tma_store_2d(&tmap_out, slab, col0, m0);
+                        if (two) tma_store_2d(&tmap_aux, slab + kGemmSlab, col0, m0);
+                    }
+                    tma_store_commit();  // one bulk group per step, even when empty: wait_group counts groups
+                    if (has_in) {
+                        // the slot of step g-1 is drained once every group but the newest has been read:
+                        // refill it with the input of step g-1+R
+                        tma_store_wait_read<1>();
+                        issue_in(g - 1 + R);
+                    }
+                }
+            }
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+        if (issuer) tma_store_wait_all();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // neither CTA may exit (or free TMEM) while the other still reads its memory / signals it
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_2sm(tmem_base, 512);
     }
 }
 
