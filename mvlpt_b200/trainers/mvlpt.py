@@ -421,9 +421,8 @@ class CustomCLIP(nn.Module):
         _require_cuda(image, "CustomCLIP")
         pl = self.prompt_learner
         dev = image.device
-        image = image.contiguous()
-        if image.dtype not in (torch.float16, torch.float32):
-            image = image.float()
+        # a batch staged by the trainer on its copy stream carries the event that marks the end of its host->device copy
+        ready = getattr(image, "_mvlpt_ready", None)
         B, C = image.shape[0], pl.n_cls
         ctx, vpt, deep = pl.forward_mvlpt_proj(self.dtype)
         if not pl.vpt_deep:
@@ -434,13 +433,19 @@ class CustomCLIP(nn.Module):
         self._txt_train = bool(train and ctx is not None)
         self._shapes = dict(B=B, C=C, v=0 if vpt is None else vpt.shape[1],
                             n_deep=None if deep is None else deep.shape[0], Lt=pl._emb.shape[1])
-        img_feat = self.image_encoder.tower(dev).forward(image, vpt, deep, train=self._img_train)
         head = self.head(dev)
+        # the text tower does not depend on the images: it runs first, while the batch is still crossing PCIe
         if ctx is not None or not (self.cache_text_features and self._txt_cache_valid == (B, C)):
             txt_feat = self.text_encoder.tower(dev).forward(pl._emb, ctx, pl._slot, pl._eot_rows, pl.coop_n_ctx, pl.csc,
                                                             train=self._txt_train)
             head.normalize_text(txt_feat, B)
             self._txt_cache_valid = (B, C) if ctx is None else False
+        if ready is not None:
+            torch.cuda.current_stream().wait_event(ready)
+        image = image.contiguous()
+        if image.dtype not in (torch.float16, torch.float32):
+            image = image.float()
+        img_feat = self.image_encoder.tower(dev).forward(image, vpt, deep, train=self._img_train)
         logits = head.logits(img_feat, C)
         t_dev, ranges = self._task_dev(task, dev)
         if t_dev is not None:
@@ -652,9 +657,30 @@ class MVLPT:
             inp_key, lab_key, task_key = 0, 1, 3
         input, label = batch[inp_key], batch[lab_key]
         tasks = batch[task_key] if self.multi_task else None
-        input = input.to(self.device, non_blocking=True)
+        input = self._stage_input(input)
         label = label.to(self.device, non_blocking=True)
         return input, label, tasks
+
+    def _stage_input(self, input: torch.Tensor) -> torch.Tensor:
+        """Host->device copy of the image batch.  A pinned host batch is copied on a dedicated copy stream into a
+        persistent device buffer and tagged with the event that ends the copy: CustomCLIP runs the (image-independent)
+        text tower first and only then waits for it, so the PCIe transfer hides behind compute.  Anything else takes
+        the reference's plain `.to(device)` route (trainers/mvlpt.py:959-960)."""
+        if input.device.type != "cpu" or not input.is_pinned():
+            return input.to(self.device, non_blocking=True)
+        key = (tuple(input.shape), input.dtype)
+        if getattr(self, "_stage_key", None) != key:
+            self._stage_key = key
+            self._stage_buf = torch.empty(input.shape, dtype=input.dtype, device=self.device)
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        cs.wait_stream(torch.cuda.current_stream(self.device))  # the previous step's readers of the buffer are done
+        with torch.cuda.stream(cs):
+            self._stage_buf.copy_(input, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._stage_buf._mvlpt_ready = ev
+        return self._stage_buf
 
     def parse_batch_train(self, batch):
         return self._parse(batch)
