@@ -15,6 +15,8 @@ What is deliberately different (result-identical):
 """
 from __future__ import annotations
 
+import os
+
 import math
 from collections import OrderedDict
 from functools import reduce
@@ -385,6 +387,11 @@ class CustomCLIP(nn.Module):
         self.grad_scale = GRAD_SCALE
         self.cache_text_features = True
         self._txt_cache_valid = False
+        # data-parallel group (set by the trainer).  With more than one rank the text tower is CLASS-SHARDED: rank r
+        # encodes classes dp.shard(n_cls), features are all-gathered, their gradients reduce-scattered
+        self.dp = None
+        self.shard_text = os.environ.get("MVLPT_SHARD_TEXT", "1") != "0"
+        self._shard_cache = {}
         self._head: Optional[E.LogitHead] = None
         self._embed_dim = clip_model.visual.output_dim
 
@@ -409,6 +416,26 @@ class CustomCLIP(nn.Module):
         if self._head is None:
             self._head = E.LogitHead(float(self.logit_scale), self._embed_dim, device)
         return self._head
+
+    def _text_shard(self, device):
+        """Class range of this rank and the exchange buffers of the class-sharded text tower (None when not sharded)."""
+        dp = self.dp
+        if dp is None or not self.shard_text or dp.world <= 1:
+            return None
+        pl = self.prompt_learner
+        C, Lt, e = pl.n_cls, pl._emb.shape[1], self._embed_dim
+        key = (C, Lt, dp.world, dp.rank, str(device))
+        if key not in self._shard_cache:
+            ranges = [dp.shard(C, r) for r in range(dp.world)]
+            c0, c1 = ranges[dp.rank]
+            cmax = max(b - a for a, b in ranges)
+            z = lambda *sz, dt=torch.float32: torch.zeros(*sz, device=device, dtype=dt)
+            self._shard_cache[key] = dict(
+                range=(c0, c1), ranges=ranges, cmax=cmax,
+                eot_rows=(pl._eot_rows[c0:c1] - c0 * Lt).to(torch.int32).contiguous(),
+                send=z(cmax, e), gathered=z(dp.world, cmax, e), full=z(C, e),
+                g_send=z(dp.world, cmax, e, dt=torch.float16), g_recv=z(cmax, e, dt=torch.float16))
+        return self._shard_cache[key]
 
     def _task_dev(self, task, device):
         if task is None or not self.multi_task_label_pertask:
@@ -436,8 +463,22 @@ class CustomCLIP(nn.Module):
         head = self.head(dev)
         # the text tower does not depend on the images: it runs first, while the batch is still crossing PCIe
         if ctx is not None or not (self.cache_text_features and self._txt_cache_valid == (B, C)):
-            txt_feat = self.text_encoder.tower(dev).forward(pl._emb, ctx, pl._slot, pl._eot_rows, pl.coop_n_ctx, pl.csc,
-                                                            train=self._txt_train)
+            sh = self._text_shard(dev)
+            tt = self.text_encoder.tower(dev)
+            if sh is None:
+                txt_feat = tt.forward(pl._emb, ctx, pl._slot, pl._eot_rows, pl.coop_n_ctx, pl.csc, train=self._txt_train)
+            else:
+                c0, c1 = sh["range"]
+                ctx_l = ctx[c0:c1] if (ctx is not None and pl.csc) else ctx
+                if c1 > c0:
+                    local = tt.forward(pl._emb[c0:c1], ctx_l, pl._slot[c0:c1], sh["eot_rows"], pl.coop_n_ctx, pl.csc,
+                                       train=self._txt_train)
+                    sh["send"][:c1 - c0].copy_(local)
+                self.dp.all_gather_into(sh["gathered"], sh["send"])
+                txt_feat = sh["full"]
+                for r, (a, b) in enumerate(sh["ranges"]):  # drop the padding rows of each rank's slab
+                    if b > a:
+                        txt_feat[a:b].copy_(sh["gathered"][r, :b - a])
             head.normalize_text(txt_feat, B)
             self._txt_cache_valid = (B, C) if ctx is None else False
         if ready is not None:
@@ -503,7 +544,20 @@ class CustomCLIP(nn.Module):
                 d_ctx = pl.upt().grad_input_views()[0]
             else:
                 d_ctx = views["ctx"]
-            tt.backward(bf["dtfeat16"], C, Lt, pl._eot_rows, pl._ctx_pos, pl.coop_n_ctx, pl.csc, d_ctx, inv)
+            sh = self._text_shard(dev)
+            if sh is None:
+                tt.backward(bf["dtfeat16"], C, Lt, pl._eot_rows, pl._ctx_pos, pl.coop_n_ctx, pl.csc, d_ctx, inv)
+            else:
+                # every rank holds d(loss)/d(text features) of ITS images for ALL classes: sum over ranks, keep my classes
+                for r, (a, b) in enumerate(sh["ranges"]):
+                    if b > a:
+                        sh["g_send"][r, :b - a].copy_(bf["dtfeat16"][a:b])
+                self.dp.reduce_scatter_sum(sh["g_recv"], sh["g_send"])
+                c0, c1 = sh["range"]
+                ops.zero(d_ctx)  # class-specific contexts: the other ranks' rows stay zero for the final all-reduce
+                if c1 > c0:
+                    tt.backward(sh["g_recv"][:c1 - c0], c1 - c0, Lt, sh["eot_rows"], pl._ctx_pos[c0:c1], pl.coop_n_ctx,
+                                pl.csc, d_ctx[c0:c1] if pl.csc else d_ctx, inv)
         if proj:
             pl.upt().backward(views)
             grads = dict(views)
@@ -625,6 +679,7 @@ class MVLPT:
             sd = torch.load(cfg.MODEL.INIT_WEIGHTS, map_location="cpu")
             self.model.prompt_learner.load_state_dict(sd.get("state_dict", sd), strict=False)
         self.model.to(self.device)
+        self.model.dp = self.dp
         self.optim = R.build_optimizer(self.model._trainables(), cfg.OPTIM)
         self.sched = R.build_lr_scheduler(self.optim, cfg.OPTIM)
         self.register_model("prompt_learner", self.model.prompt_learner, self.optim, self.sched)

@@ -215,8 +215,25 @@ class DataParallelGroup:
         if self.enabled and self.world > 1:
             self.dist.barrier(group=self.group)
 
-    def shard(self, n: int) -> Tuple[int, int]:
-        """[start, end) of this rank's slice of n items (balanced, contiguous)."""
+    def shard(self, n: int, rank: Optional[int] = None) -> Tuple[int, int]:
+        """[start, end) of a rank's slice of n items (balanced, contiguous); this rank's by default."""
+        rank = self.rank if rank is None else rank
         base, rem = divmod(n, self.world)
-        start = self.rank * base + min(self.rank, rem)
-        return start, start + base + (1 if self.rank < rem else 0)
+        start = rank * base + min(rank, rem)
+        return start, start + base + (1 if rank < rem else 0)
+
+    def all_gather_into(self, out: torch.Tensor, send: torch.Tensor) -> torch.Tensor:
+        """out[r] = rank r's `send` (out: [world, *send.shape]) — the text-feature exchange of the class-sharded tower."""
+        if self.enabled and self.world > 1:
+            self.dist.all_gather_into_tensor(out.view(-1), send.view(-1), group=self.group)
+        else:
+            out.view(-1).copy_(send.view(-1))
+        return out
+
+    def reduce_scatter_sum(self, out: torch.Tensor, send: torch.Tensor) -> torch.Tensor:
+        """out = sum over ranks of their send[this rank] (send: [world, *out.shape])."""
+        if self.enabled and self.world > 1:
+            self.dist.reduce_scatter_tensor(out.view(-1), send.view(-1), op=self.dist.ReduceOp.SUM, group=self.group)
+        else:
+            out.view(-1).copy_(send.view(-1))
+        return out

@@ -152,6 +152,26 @@ assert torch.allclose(mine, full, atol=1e-6)
 t = torch.tensor([float(dp.rank + 1)], dtype=torch.float64)
 dp.all_reduce_max(t)
 assert float(t) == 2.0
+# class-sharded text tower (SURVEY.md 8e): per-rank class ranges tile [0, C); padded all-gather of the features;
+# reduce-scatter of their gradients gives every rank the SUM over ranks for its own classes
+C, e = 7, 3
+ranges = [dp.shard(C, r) for r in range(dp.world)]
+assert ranges[0][0] == 0 and ranges[-1][1] == C and all(ranges[i][1] == ranges[i + 1][0] for i in range(dp.world - 1))
+cmax = max(b - a for a, b in ranges)
+feats = torch.arange(C * e, dtype=torch.float32).view(C, e)           # what a single process would compute
+c0, c1 = ranges[dp.rank]
+send = torch.zeros(cmax, e); send[:c1 - c0] = feats[c0:c1]
+gathered = torch.zeros(dp.world, cmax, e)
+dp.all_gather_into(gathered, send)
+full = torch.cat([gathered[r, :b - a] for r, (a, b) in enumerate(ranges)])
+assert torch.equal(full, feats)
+g_local = torch.full((C, e), float(dp.rank + 1))                      # d(loss)/d(features) from this rank's images
+g_send = torch.zeros(dp.world, cmax, e)
+for r, (a, b) in enumerate(ranges):
+    g_send[r, :b - a] = g_local[a:b]
+g_recv = torch.zeros(cmax, e)
+dp.reduce_scatter_sum(g_recv, g_send)
+assert torch.equal(g_recv[:c1 - c0], torch.full((c1 - c0, e), 3.0)), g_recv
 dp.barrier()
 print("rank", dp.rank, "ok")
 """
