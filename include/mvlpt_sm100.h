@@ -83,7 +83,9 @@ int mvlpt_fmha_force_legacy(int on);
  * row (trainers/mvlpt.py:124-128).  d % 4 == 0, d <= 1024.
  * Backward (gamma/beta frozen, trainers/mvlpt.py:856-858): dx = rstd*(g - mean(g) - xhat*mean(g*xhat)),
  * g = dy*gamma; written (accumulate=0) or added (accumulate=1) to the fp32 gradient stream at the same rows,
- * with an optional fp16 copy dx16 of the result (operand of the next dgrad GEMM).
+ * with an optional fp16 copy dx16 of the result (operand of the next dgrad GEMM).  dx_stream NULL selects the
+ * fp16 gradient stream: the running sum is read from and written to dx16 alone (the reference's own precision:
+ * its residual gradients are fp16 tensors), which cuts the kernel's HBM traffic from 16 to 10 bytes per element.
  * ------------------------------------------------------------------------------------------------ */
 int mvlpt_ln_fwd(const void* x, const void* row_index, const void* gamma, const void* beta, void* y, int rows, int d,
                  float eps, mvlpt_stream_t stream);
@@ -102,6 +104,7 @@ int mvlpt_ln_bwd(const void* dy, const void* x, const void* row_index, const voi
  *   (trainers/mvlpt.py:73-82).
  * mvlpt_prompt_grad: grad[j] = inv_scale * sum_b dx[b,1+j] (autograd of the expand over B); with zero_rows the
  *   rows are then cleared in dx (and dx16) because the replaced rows have no upstream.
+ *   dx NULL = fp16 gradient stream: the rows are read from dx16.
  * ------------------------------------------------------------------------------------------------ */
 int mvlpt_im2col(const void* img, int img_f32, void* patches, int B, int H, int W, int p, int Kp, mvlpt_stream_t stream);
 int mvlpt_embed_assemble(const void* pe, const void* cls, const void* pos, const void* gamma, const void* beta,
@@ -117,11 +120,12 @@ int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int
  * trainers/mvlpt.py:107/112).  emb fp32 [C, Lt, d] = token_embedding(tokenised "X .. X name.");
  * slot int32 [C, Lt]: >= 0 selects context vector `slot` (of class c when csc), -1 keeps emb.  The map encodes
  * end / middle / front placement, so no per-class Python loop is needed.  ctx NULL = fixed prompt.
- * mvlpt_ctx_grad: grad[j] = inv_scale * sum_c dx0[c, ctx_pos[c,j]]  (or per class when csc); ctx_pos int32 [C,n].
+ * mvlpt_ctx_grad: grad[j] = inv_scale * sum_c dx0[c, ctx_pos[c,j]]  (or per class when csc); ctx_pos int32 [C,n];
+ *   dx0 is the fp32 gradient stream, or the fp16 one when dx_f16.
  * ------------------------------------------------------------------------------------------------ */
 int mvlpt_text_assemble(const void* emb, const void* ctx, int ctx_f16, const void* slot, const void* pos, void* x0,
                         int C, int Lt, int n_ctx, int d, int csc, mvlpt_stream_t stream);
-int mvlpt_ctx_grad(const void* dx0, const void* ctx_pos, void* grad, int C, int Lt, int n_ctx, int d, int csc,
+int mvlpt_ctx_grad(const void* dx0, int dx_f16, const void* ctx_pos, void* grad, int C, int Lt, int n_ctx, int d, int csc,
                    float inv_scale, mvlpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------

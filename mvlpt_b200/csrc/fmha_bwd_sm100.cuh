@@ -86,7 +86,8 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t* acc_full = bars + 8;  // dK / dV of a key chunk (and every earlier MMA) complete
     uint64_t* acc_free = bars + 9;  // the epilogue warps have read the accumulators of a key chunk out of TMEM
     uint64_t* d_full = bars + 10;   // per-query statistics (D, lse) of a unit are in shared memory
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 11);
+    uint64_t* kv1_full = bars + 11; // {K1,V1} landed (load group 1 is requested in two parts: {Q1,dO1} is needed first)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Lp = p.Lp, d = p.d, QT = p.QT, KC = p.KC, NQH = p.NQH;
@@ -110,6 +111,7 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_init(acc_full, 1);
         mbar_init(acc_free, 128);
         mbar_init(d_full, 128);
+        mbar_init(kv1_full, 1);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -129,11 +131,15 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 const int h = unit % p.heads, n = unit / p.heads;
                 for (int g = 0; g < QT; ++g) {  // QT == KC: group g = {Q_g, dO_g, K_g, V_g}
                     if (it > 0) mbar_wait(&g_free[g], (uint32_t)(it - 1) & 1);
-                    mbar_arrive_expect_tx(&ld_full[g], 65536u);
+                    // group 1 arrives right at the unit boundary: {Q1,dO1} (first used by step 3) goes first and has
+                    // its own barrier, {K1,V1} (first used by step NQH+1) follows
+                    uint64_t* kv_bar = g ? kv1_full : &ld_full[0];
+                    mbar_arrive_expect_tx(&ld_full[g], g ? 32768u : 65536u);
                     tma_load_3d(sQ + g * 16384, &tmap_q, &ld_full[g], h * 64, g * 128, n);
-                    tma_load_3d(sK + g * 16384, &tmap_q, &ld_full[g], d + h * 64, g * 128, n);
                     tma_load_3d(sdO + g * 16384, &tmap_do, &ld_full[g], h * 64, g * 128, n);
-                    tma_load_3d(sV + g * 16384, &tmap_q, &ld_full[g], 2 * d + h * 64, g * 128, n);
+                    if (g) mbar_arrive_expect_tx(kv1_full, 32768u);
+                    tma_load_3d(sK + g * 16384, &tmap_q, kv_bar, d + h * 64, g * 128, n);
+                    tma_load_3d(sV + g * 16384, &tmap_q, kv_bar, 2 * d + h * 64, g * 128, n);
                 }
             }
         }
@@ -175,7 +181,7 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             tc_fence_after();
             if (leader) FMHA_DBG(0, 2);
             issue_st(0, 0, gi & 1);
-            bool g1_ready = false;
+            bool g1_ready = false, kv1_ready = false;
             for (int kc = 0; kc < KC; ++kc) {
                 const int nk = (Lp - kc * 128) < 128 ? (Lp - kc * 128) : 128;
                 for (int qh = 0; qh < NQH; ++qh, ++gi) {
@@ -186,10 +192,15 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                         const int nqh = (qh + 1 == NQH) ? 0 : qh + 1;
                         const int nkc = (qh + 1 == NQH) ? kc + 1 : kc;
                         if (nkc < KC) {
-                            if (!g1_ready && (nkc > 0 || nqh >= 2)) {  // first touch of load group 1
+                            if (!g1_ready && nqh >= 2) {  // first touch of {Q1,dO1}
                                 mbar_wait(&ld_full[1], (uint32_t)it & 1);
                                 tc_fence_after();
                                 g1_ready = true;
+                            }
+                            if (!kv1_ready && nkc > 0) {  // first touch of {K1,V1}
+                                mbar_wait(kv1_full, (uint32_t)it & 1);
+                                tc_fence_after();
+                                kv1_ready = true;
                             }
                             issue_st(nkc, nqh, b ^ 1);
                         }

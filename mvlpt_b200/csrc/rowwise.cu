@@ -142,7 +142,10 @@ __global__ void ln_bwd_kernel(const __half* __restrict__ dy, const float* __rest
     s1 = wsum(s1) / d;
     s2 = wsum(s2) / d;
     Row out;
-    if (accumulate) row_load(out, dx_stream + dst * d, d, lane);
+    if (accumulate) {
+        if (dx_stream) row_load(out, dx_stream + dst * d, d, lane);
+        else row_load_h(out, dx16 + dst * d, d, lane);  // fp16 gradient stream: the running sum lives in dx16
+    }
 #pragma unroll
     for (int i = 0; i < kMaxV4; ++i) {
         const float4 a = g.v[i], h = xr.v[i];
@@ -151,8 +154,95 @@ __global__ void ln_bwd_kernel(const __half* __restrict__ dy, const float* __rest
         if (accumulate) { o.x += out.v[i].x; o.y += out.v[i].y; o.z += out.v[i].z; o.w += out.v[i].w; }
         out.v[i] = o;
     }
-    row_store(out, dx_stream + dst * d, d, lane);
+    if (dx_stream) row_store(out, dx_stream + dst * d, d, lane);
     if (dx16) row_store_h(out, dx16 + dst * d, d, lane);
+}
+
+// Fast path of the above for d == NV*128 without a row gather: every load of the row (x, dy and the running gradient)
+// is issued before the first use, so one warp keeps up to 10*d bytes in flight instead of serialising three round
+// trips to HBM behind the two warp reductions; statistics from sum / sum of squares in one pass over registers.
+template <int NV, bool STREAM_F32>
+__global__ void __launch_bounds__(256)
+ln_bwd_fast_kernel(const __half* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
+                   float* __restrict__ dx_stream, __half* __restrict__ dx16, int rows, float eps, int accumulate) {
+    constexpr int d = NV * 128;
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const size_t base = (size_t)r * d + lane * 4;
+    float4 xv[NV], run[NV];
+    uint2 gy[NV], run16[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) xv[i] = *reinterpret_cast<const float4*>(x + base + i * 128);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) gy[i] = *reinterpret_cast<const uint2*>(dy + base + i * 128);
+    if (accumulate) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            if (STREAM_F32) run[i] = *reinterpret_cast<const float4*>(dx_stream + base + i * 128);
+            else run16[i] = *reinterpret_cast<const uint2*>(dx16 + base + i * 128);
+        }
+    }
+    // statistics of x (fp32, biased variance around the mean)
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s += xv[i].x + xv[i].y + xv[i].z + xv[i].w;
+    const float mean = wsum(s) * (1.f / d);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        xv[i].x -= mean; xv[i].y -= mean; xv[i].z -= mean; xv[i].w -= mean;
+        q += xv[i].x * xv[i].x + xv[i].y * xv[i].y + xv[i].z * xv[i].z + xv[i].w * xv[i].w;
+    }
+    const float rstd = rsqrtf(wsum(q) * (1.f / d) + eps);
+    float4 g[NV];
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const float4 gg = *reinterpret_cast<const float4*>(gamma + lane * 4 + i * 128);
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&gy[i].x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&gy[i].y));
+        g[i] = make_float4(a.x * gg.x, a.y * gg.y, b.x * gg.z, b.y * gg.w);
+        xv[i].x *= rstd; xv[i].y *= rstd; xv[i].z *= rstd; xv[i].w *= rstd;  // xhat
+        s1 += g[i].x + g[i].y + g[i].z + g[i].w;
+        s2 += g[i].x * xv[i].x + g[i].y * xv[i].y + g[i].z * xv[i].z + g[i].w * xv[i].w;
+    }
+    s1 = wsum(s1) * (1.f / d);
+    s2 = wsum(s2) * (1.f / d);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        float4 o = make_float4(rstd * (g[i].x - s1 - xv[i].x * s2), rstd * (g[i].y - s1 - xv[i].y * s2),
+                               rstd * (g[i].z - s1 - xv[i].z * s2), rstd * (g[i].w - s1 - xv[i].w * s2));
+        if (accumulate) {
+            if (STREAM_F32) {
+                o.x += run[i].x; o.y += run[i].y; o.z += run[i].z; o.w += run[i].w;
+            } else {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&run16[i].x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&run16[i].y));
+                o.x += a.x; o.y += a.y; o.z += b.x; o.w += b.y;
+            }
+        }
+        if (STREAM_F32) *reinterpret_cast<float4*>(dx_stream + base + i * 128) = o;
+        if (dx16) {
+            uint2 u;
+            *reinterpret_cast<__half2*>(&u.x) = __floats2half2_rn(o.x, o.y);
+            *reinterpret_cast<__half2*>(&u.y) = __floats2half2_rn(o.z, o.w);
+            *reinterpret_cast<uint2*>(dx16 + base + i * 128) = u;
+        }
+    }
+}
+
+template <int NV>
+static void launch_ln_bwd_fast(const void* dy, const void* x, const void* gamma, void* dx_stream, void* dx16, int rows,
+                               float eps, int accumulate, cudaStream_t s) {
+    if (dx_stream)
+        ln_bwd_fast_kernel<NV, true><<<cdiv(rows, 8), 256, 0, s>>>(static_cast<const __half*>(dy), static_cast<const float*>(x),
+                                                                  static_cast<const float*>(gamma), static_cast<float*>(dx_stream),
+                                                                  static_cast<__half*>(dx16), rows, eps, accumulate);
+    else
+        ln_bwd_fast_kernel<NV, false><<<cdiv(rows, 8), 256, 0, s>>>(static_cast<const __half*>(dy), static_cast<const float*>(x),
+                                                                   static_cast<const float*>(gamma), nullptr,
+                                                                   static_cast<__half*>(dx16), rows, eps, accumulate);
 }
 
 // ---------------------------------------------------------------- im2col for the patch-embedding conv
@@ -227,12 +317,20 @@ __global__ void prompt_grad_kernel(float* __restrict__ dx, __half* __restrict__ 
     if (c >= d) return;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int b = 0; b < B; ++b) {
-        float* p = dx + ((size_t)b * L + 1 + j) * d + c;
-        const float4 t = *reinterpret_cast<const float4*>(p);
+        const size_t off = ((size_t)b * L + 1 + j) * d + c;
+        float4 t;
+        if (dx) {
+            t = *reinterpret_cast<const float4*>(dx + off);
+        } else {  // fp16 gradient stream
+            const uint2 u = *reinterpret_cast<const uint2*>(dx16 + off);
+            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+            t = make_float4(lo.x, lo.y, hi.x, hi.y);
+        }
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
         if (zero_rows) {
-            *reinterpret_cast<float4*>(p) = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (dx16) *reinterpret_cast<uint2*>(dx16 + ((size_t)b * L + 1 + j) * d + c) = make_uint2(0u, 0u);
+            if (dx) *reinterpret_cast<float4*>(dx + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(0u, 0u);
         }
     }
     *reinterpret_cast<float4*>(grad + (size_t)j * d + c) =
@@ -266,21 +364,29 @@ __global__ void text_assemble_kernel(const float* __restrict__ emb, const void* 
 }
 
 // grad_ctx[j] = inv_scale * sum_c dx0[c, ctx_pos[c,j]]   (shared context)   or per class when csc
-__global__ void ctx_grad_kernel(const float* __restrict__ dx0, const int* __restrict__ ctx_pos, float* __restrict__ grad,
-                                int C, int Lt, int n_ctx, int d, int csc, float inv_scale) {
+__device__ __forceinline__ float4 load4_any(const void* base, size_t off, int f16) {
+    if (!f16) return *reinterpret_cast<const float4*>(static_cast<const float*>(base) + off);
+    const uint2 u = *reinterpret_cast<const uint2*>(static_cast<const __half*>(base) + off);
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+
+__global__ void ctx_grad_kernel(const void* __restrict__ dx0, int dx_f16, const int* __restrict__ ctx_pos,
+                                float* __restrict__ grad, int C, int Lt, int n_ctx, int d, int csc, float inv_scale) {
     const int j = blockIdx.y;
     const int col = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (col >= d) return;
     if (csc) {
         const int c = blockIdx.z;
-        const float4 t = *reinterpret_cast<const float4*>(dx0 + ((size_t)c * Lt + ctx_pos[c * n_ctx + j]) * d + col);
+        const float4 t = load4_any(dx0, ((size_t)c * Lt + ctx_pos[c * n_ctx + j]) * d + col, dx_f16);
         *reinterpret_cast<float4*>(grad + ((size_t)c * n_ctx + j) * d + col) =
             make_float4(t.x * inv_scale, t.y * inv_scale, t.z * inv_scale, t.w * inv_scale);
         return;
     }
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int c = 0; c < C; ++c) {
-        const float4 t = *reinterpret_cast<const float4*>(dx0 + ((size_t)c * Lt + ctx_pos[c * n_ctx + j]) * d + col);
+        const float4 t = load4_any(dx0, ((size_t)c * Lt + ctx_pos[c * n_ctx + j]) * d + col, dx_f16);
         acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
     }
     *reinterpret_cast<float4*>(grad + (size_t)j * d + col) =
@@ -311,11 +417,18 @@ int mvlpt_ln_fwd(const void* x, const void* row_index, const void* gamma, const 
 
 int mvlpt_ln_bwd(const void* dy, const void* x, const void* row_index, const void* gamma, void* dx_stream, void* dx16,
                  int rows, int d, float eps, int accumulate, mvlpt_stream_t stream) {
-    if (!dy || !x || !gamma || !dx_stream) return fail(MVLPT_EINVAL, "mvlpt_ln_bwd: null argument");
+    if (!dy || !x || !gamma || (!dx_stream && !dx16)) return fail(MVLPT_EINVAL, "mvlpt_ln_bwd: null argument");
     if (rows <= 0) return fail(MVLPT_EINVAL, "mvlpt_ln_bwd: rows must be positive");
     int rc = check_d(d, "mvlpt_ln_bwd");
     if (rc) return rc;
     if ((rc = require_sm100())) return rc;
+    if (!row_index && (d == 512 || d == 768 || d == 1024)) {
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        if (d == 512) launch_ln_bwd_fast<4>(dy, x, gamma, dx_stream, dx16, rows, eps, accumulate, s);
+        else if (d == 768) launch_ln_bwd_fast<6>(dy, x, gamma, dx_stream, dx16, rows, eps, accumulate, s);
+        else launch_ln_bwd_fast<8>(dy, x, gamma, dx_stream, dx16, rows, eps, accumulate, s);
+        return launched("ln_bwd");
+    }
     ln_bwd_kernel<<<cdiv(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const __half*>(dy), static_cast<const float*>(x), static_cast<const int*>(row_index),
         static_cast<const float*>(gamma), static_cast<float*>(dx_stream), static_cast<__half*>(dx16), rows, d, eps,
@@ -372,7 +485,7 @@ int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, in
 
 int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int d, float inv_scale, int zero_rows,
                       mvlpt_stream_t stream) {
-    if (!dx || !grad) return fail(MVLPT_EINVAL, "mvlpt_prompt_grad: null argument");
+    if ((!dx && !dx16) || !grad) return fail(MVLPT_EINVAL, "mvlpt_prompt_grad: null argument");
     if (B <= 0 || v <= 0 || L < 1 + v) return fail(MVLPT_EINVAL, "mvlpt_prompt_grad: bad sizes");
     int rc = check_d(d, "mvlpt_prompt_grad");
     if (rc) return rc;
@@ -396,7 +509,7 @@ int mvlpt_text_assemble(const void* emb, const void* ctx, int ctx_f16, const voi
     return launched("text_assemble");
 }
 
-int mvlpt_ctx_grad(const void* dx0, const void* ctx_pos, void* grad, int C, int Lt, int n_ctx, int d, int csc,
+int mvlpt_ctx_grad(const void* dx0, int dx_f16, const void* ctx_pos, void* grad, int C, int Lt, int n_ctx, int d, int csc,
                    float inv_scale, mvlpt_stream_t stream) {
     if (!dx0 || !ctx_pos || !grad) return fail(MVLPT_EINVAL, "mvlpt_ctx_grad: null argument");
     if (C <= 0 || Lt <= 0 || n_ctx <= 0) return fail(MVLPT_EINVAL, "mvlpt_ctx_grad: bad sizes");
@@ -405,8 +518,7 @@ int mvlpt_ctx_grad(const void* dx0, const void* ctx_pos, void* grad, int C, int 
     if ((rc = require_sm100())) return rc;
     dim3 grid(cdiv(d / 4, 64), n_ctx, csc ? C : 1);
     ctx_grad_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const float*>(dx0), static_cast<const int*>(ctx_pos), static_cast<float*>(grad), C, Lt, n_ctx, d,
-        csc, inv_scale);
+        dx0, dx_f16, static_cast<const int*>(ctx_pos), static_cast<float*>(grad), C, Lt, n_ctx, d, csc, inv_scale);
     return launched("ctx_grad");
 }
 

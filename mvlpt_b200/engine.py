@@ -11,7 +11,8 @@ HBM layout (N sequences of L tokens, M = N*L, width d):
   LN output h          fp16 [M, d]    workspace, consumed at once by the next GEMM
   qkv / attention out  fp16 [M, 3d] / [M, d], lse fp32 [N, heads, L]     saved per block when training
   FC1 pre-activation t fp16 [M, 4d]   saved per block when training; QuickGELU output g is a workspace
-  gradient stream      fp32 [M, d] (+ fp16 copy as GEMM operand), dt [M,4d], dh [M,d], dqkv [M,3d] fp16
+  gradient stream      fp16 [M, d] (GEMM operand and running sum; optional fp32 running sum), dt [M,4d], dh [M,d],
+                       dqkv [M,3d] fp16
 Gradients are carried multiplied by `grad_scale` (power of two) so the fp16 operands of the dgrad GEMMs stay in
 range; the prompt-gradient reductions divide it out in fp32.
 
@@ -20,6 +21,7 @@ torch is used for device memory, streams and (optionally) CUDA-graph capture onl
 from __future__ import annotations
 
 import math
+import os
 from typing import Dict, List, Optional, Sequence
 
 import torch
@@ -27,6 +29,12 @@ import torch
 from . import ops
 
 F16, F32, I32 = torch.float16, torch.float32, torch.int32
+
+# Precision of the running residual GRADIENT between blocks.  fp16 (default) is the reference's own (its activations and
+# their gradients are fp16 tensors) and costs 10 instead of 16 bytes per element in every LayerNorm backward;
+# MVLPT_GRAD_STREAM_F32=1 keeps an fp32 running sum next to the fp16 GEMM operand.  Either way every sum inside a kernel
+# is fp32 and the values are scaled by `grad_scale`.
+GRAD_STREAM_F32 = os.environ.get("MVLPT_GRAD_STREAM_F32", "0") == "1"
 
 
 def _round_up(a: int, b: int) -> int:
@@ -74,7 +82,7 @@ class TowerBuffers:
         self.t = [e(M, 4 * d) for _ in range(nsave)] if train else None
         self.g = e(M, 4 * d)
         if train:
-            self.dx = e(M, d, dt=F32)
+            self.dx = e(M, d, dt=F32) if GRAD_STREAM_F32 else None  # fp32 running gradient (optional, see above)
             self.dx16 = e(M, d)
             self.dt = e(M, 4 * d)
             self.dh = e(M, d)
@@ -205,7 +213,8 @@ class ImageTower:
         bf = self.buffers(B, v, True)
         a: TowerBuffers = bf["act"]
         ops.gemm(dfeat16, self.proj, bf["dpool"])
-        ops.zero(a.dx)
+        if a.dx is not None:
+            ops.zero(a.dx)
         ops.zero(a.dx16)
         ops.ln_bwd(bf["dpool"], bf["final"], self.ln_post_g, a.dx, a.dx16, B, self.d, accumulate=False,
                    row_index=bf["cls_idx"])
@@ -213,7 +222,7 @@ class ImageTower:
             block_backward(self.blocks[l], a, l, causal=False)
             if n_deep is not None and l >= 1:
                 ops.prompt_grad(a.dx, a.dx16, grad_deep[l - 1], B, a.L, v, self.d, inv_scale, zero_rows=True)
-        ops.prompt_grad(a.dx, None, grad_vpt, B, a.L, v, self.d, inv_scale, zero_rows=False)
+        ops.prompt_grad(a.dx, None if a.dx is not None else a.dx16, grad_vpt, B, a.L, v, self.d, inv_scale, zero_rows=False)
 
 
 class TextTower:
@@ -267,12 +276,13 @@ class TextTower:
         bf = self.buffers(C, Lt, True)
         a: TowerBuffers = bf["act"]
         ops.gemm(dfeat16, self.proj, bf["dpool"])
-        ops.zero(a.dx)
+        if a.dx is not None:
+            ops.zero(a.dx)
         ops.zero(a.dx16)
         ops.ln_bwd(bf["dpool"], bf["final"], self.ln_g, a.dx, a.dx16, C, self.d, accumulate=False, row_index=eot_rows)
         for l in reversed(range(self.layers)):
             block_backward(self.blocks[l], a, l, causal=True)
-        ops.ctx_grad(a.dx, ctx_pos, grad_ctx, C, Lt, n_ctx, self.d, csc, inv_scale)
+        ops.ctx_grad(a.dx if a.dx is not None else a.dx16, ctx_pos, grad_ctx, C, Lt, n_ctx, self.d, csc, inv_scale)
 
 
 class LogitHead:

@@ -122,7 +122,11 @@ def ln_bwd(dy, x, gamma, dx_stream, dx16, rows, d, accumulate, row_index=None):
     check(_lib.lib().mvlpt_ln_bwd(_p(dy), _p(x), _p(row_index), _p(gamma), _p(dx_stream), _p(dx16), rows, d, LN_EPS,
                                   int(accumulate), _stream()), "mvlpt_ln_bwd")
     if t0 is not None:
-        PROFILER.end("ln_bwd", t0, 0.0, (2.0 + 4.0 + 4.0 + (4.0 if accumulate else 0.0) + 2.0) * rows * d)
+        if dx_stream is not None:  # dy + x + dx write (+ dx read) + dx16 write
+            nbytes = (2.0 + 4.0 + 4.0 + (4.0 if accumulate else 0.0) + 2.0) * rows * d
+        else:                      # fp16 gradient stream: dy + x + dx16 write (+ dx16 read)
+            nbytes = (2.0 + 4.0 + 2.0 + (2.0 if accumulate else 0.0)) * rows * d
+        PROFILER.end("ln_bwd", t0, 0.0, nbytes)
 
 
 def im2col(img, patches, B, H, W, p, Kp):
@@ -153,8 +157,8 @@ def text_assemble(emb, ctx, slot, pos, x0, C, Lt, n_ctx, d, csc):
 
 
 def ctx_grad(dx0, ctx_pos, grad, C, Lt, n_ctx, d, csc, inv_scale):
-    check(_lib.lib().mvlpt_ctx_grad(_p(dx0), _p(ctx_pos), _p(grad), C, Lt, n_ctx, d, int(csc), float(inv_scale),
-                                    _stream()), "mvlpt_ctx_grad")
+    check(_lib.lib().mvlpt_ctx_grad(_p(dx0), int(dx0.dtype == torch.float16), _p(ctx_pos), _p(grad), C, Lt, n_ctx, d,
+                                    int(csc), float(inv_scale), _stream()), "mvlpt_ctx_grad")
 
 
 def l2norm_fwd(x, y16, y32, inv_norm, rows, e):

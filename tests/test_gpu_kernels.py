@@ -90,6 +90,12 @@ def test_layernorm_fwd_bwd(rows, d):
     ref.backward(dy.float())
     assert _rel(dx, xr.grad + 1) < 1e-4
     assert _rel(dx16.float(), xr.grad + 1) < 2e-3
+    # fp16 gradient stream (dx_stream = None): the running sum is read from / written to dx16 alone
+    run16 = torch.full((rows, d), 0.5, device="cuda", dtype=torch.half)
+    ops.ln_bwd(dy, x, g, None, run16, rows, d, accumulate=True)
+    assert _rel(run16.float(), xr.grad + 0.5) < 2e-3
+    ops.ln_bwd(dy, x, g, None, run16, rows, d, accumulate=False)
+    assert _rel(run16.float(), xr.grad) < 2e-3
 
 
 def test_ce_softlabels_taskmask_and_metrics():

@@ -94,5 +94,7 @@ if "ln" in what:
         dx16 = [torch.empty(M, d, device=dev, dtype=torch.half) for _ in range(nb)]
         t_f = timeit(lambda i: ops.ln_fwd(x[i % nb], g, bb, y[i % nb], M, d))
         t_b = timeit(lambda i: ops.ln_bwd(dy[i % nb], x[i % nb], g, dx[i % nb], dx16[i % nb], M, d, accumulate=True))
+        t_h = timeit(lambda i: ops.ln_bwd(dy[i % nb], x[i % nb], g, None, dx16[i % nb], M, d, accumulate=True))
         print(f"ln M={M} d={d}: fwd {t_f:7.1f} us ({M * d * 6 / t_f / 1e3:6.0f} GB/s)  bwd {t_b:7.1f} us "
-              f"({M * d * 16 / t_b / 1e3:6.0f} GB/s)", flush=True)
+              f"({M * d * 16 / t_b / 1e3:6.0f} GB/s)  bwd fp16-stream {t_h:7.1f} us ({M * d * 10 / t_h / 1e3:6.0f} GB/s)",
+              flush=True)
