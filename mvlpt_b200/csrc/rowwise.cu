@@ -264,6 +264,27 @@ __global__ void im2col_kernel(const T* __restrict__ img, __half* __restrict__ pa
     }
 }
 
+// fp16 images with p % 8 == 0: one thread moves 8 consecutive pixels of a patch row (16 bytes in, 16 bytes out).
+// grid.x = patches / 4, block = 4 patches x (3 * p * p / 8) threads padded to a multiple of 32.
+__global__ void im2col_vec8_kernel(const __half* __restrict__ img, __half* __restrict__ patches, int n_patches, int H, int W,
+                                   int p, int Kp, int per_patch) {
+    const int gw = W / p, gh = H / p;
+    const int local = threadIdx.x / per_patch, t = threadIdx.x % per_patch;
+    const int patch = blockIdx.x * 4 + local;
+    if (local >= 4 || patch >= n_patches) return;
+    const int b = patch / (gh * gw), rem = patch % (gh * gw), py = rem / gw, px = rem % gw;
+    const int K8 = 3 * p * p / 8;  // 16-byte units that carry pixels; [K8, Kp/8) are zero padding
+    __half* dst = patches + (size_t)patch * Kp;
+    for (int u = t; u < Kp / 8; u += per_patch) {
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (u < K8) {
+            const int k = u * 8, c = k / (p * p), r2 = k % (p * p), ky = r2 / p, kx = r2 % p;
+            v = *reinterpret_cast<const uint4*>(img + (((size_t)b * 3 + c) * H + py * p + ky) * W + px * p + kx);
+        }
+        *reinterpret_cast<uint4*>(dst + u * 8) = v;
+    }
+}
+
 // ---------------------------------------------------------------- image token assembly
 // x0[b,0] = LNpre(cls + pos[0]); x0[b,1..v] = prompt; x0[b,1+v+i] = LNpre(pe[b,i] + pos[1+i])
 __global__ void embed_assemble_kernel(const __half* __restrict__ pe, const float* __restrict__ cls,
@@ -310,31 +331,47 @@ __global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __rest
 }
 
 // grad[j, :] = inv_scale * sum_b dx[b, 1+j, :]; optionally zero those rows (they do not flow further back)
-__global__ void prompt_grad_kernel(float* __restrict__ dx, __half* __restrict__ dx16, float* __restrict__ grad, int B,
-                                   int L, int v, int d, float inv_scale, int zero_rows) {
+// Block = (prompt row j, 64 columns): 16 column groups of 4 x 16 batch lanes; every batch lane walks b = lane, lane+16, ..
+// and the 16 partial sums are added in a fixed order through shared memory (deterministic, no atomics).
+__global__ void __launch_bounds__(256)
+prompt_grad_kernel(float* __restrict__ dx, __half* __restrict__ dx16, float* __restrict__ grad, int B, int L, int v, int d,
+                   float inv_scale, int zero_rows) {
+    __shared__ float4 part[16][17];
     const int j = blockIdx.y;
-    const int c = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (c >= d) return;
+    const int cg = threadIdx.x & 15, bl = threadIdx.x >> 4;
+    const int c = (blockIdx.x * 16 + cg) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int b = 0; b < B; ++b) {
-        const size_t off = ((size_t)b * L + 1 + j) * d + c;
-        float4 t;
-        if (dx) {
-            t = *reinterpret_cast<const float4*>(dx + off);
-        } else {  // fp16 gradient stream
-            const uint2 u = *reinterpret_cast<const uint2*>(dx16 + off);
-            const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-            const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-            t = make_float4(lo.x, lo.y, hi.x, hi.y);
-        }
-        acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-        if (zero_rows) {
-            if (dx) *reinterpret_cast<float4*>(dx + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(0u, 0u);
+    if (c < d) {
+        for (int b = bl; b < B; b += 16) {
+            const size_t off = ((size_t)b * L + 1 + j) * d + c;
+            float4 t;
+            if (dx) {
+                t = *reinterpret_cast<const float4*>(dx + off);
+            } else {  // fp16 gradient stream
+                const uint2 u = *reinterpret_cast<const uint2*>(dx16 + off);
+                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                t = make_float4(lo.x, lo.y, hi.x, hi.y);
+            }
+            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
+            if (zero_rows) {
+                if (dx) *reinterpret_cast<float4*>(dx + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(0u, 0u);
+            }
         }
     }
-    *reinterpret_cast<float4*>(grad + (size_t)j * d + c) =
-        make_float4(acc.x * inv_scale, acc.y * inv_scale, acc.z * inv_scale, acc.w * inv_scale);
+    part[bl][cg] = acc;
+    __syncthreads();
+    if (bl == 0 && c < d) {
+        float4 s = part[0][cg];
+#pragma unroll
+        for (int k = 1; k < 16; ++k) {
+            const float4 t = part[k][cg];
+            s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w;
+        }
+        *reinterpret_cast<float4*>(grad + (size_t)j * d + c) =
+            make_float4(s.x * inv_scale, s.y * inv_scale, s.z * inv_scale, s.w * inv_scale);
+    }
 }
 
 // ---------------------------------------------------------------- text token assembly
@@ -445,6 +482,15 @@ int mvlpt_im2col(const void* img, int img_f32, void* patches, int B, int H, int 
     if (rc) return rc;
     const int patches_n = B * (H / p) * (W / p);
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (!img_f32 && (p % 8) == 0 && (W % 8) == 0 && (reinterpret_cast<uintptr_t>(img) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(patches) & 15) == 0) {
+        int per_patch = 3 * p * p / 8;  // one 16-byte unit per thread
+        if (per_patch > 64) per_patch = 64;
+        im2col_vec8_kernel<<<cdiv(patches_n, 4), 4 * per_patch, 0, s>>>(static_cast<const __half*>(img),
+                                                                        static_cast<__half*>(patches), patches_n, H, W, p,
+                                                                        Kp, per_patch);
+        return launched("im2col");
+    }
     if (img_f32)
         im2col_kernel<float><<<patches_n, 256, 0, s>>>(static_cast<const float*>(img), static_cast<__half*>(patches), B,
                                                        H, W, p, Kp);
@@ -490,8 +536,8 @@ int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int
     int rc = check_d(d, "mvlpt_prompt_grad");
     if (rc) return rc;
     if ((rc = require_sm100())) return rc;
-    dim3 grid(cdiv(d / 4, 64), v);
-    prompt_grad_kernel<<<grid, 64, 0, static_cast<cudaStream_t>(stream)>>>(
+    dim3 grid(cdiv(d, 64), v);
+    prompt_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<float*>(dx), static_cast<__half*>(dx16), static_cast<float*>(grad), B, L, v, d, inv_scale, zero_rows);
     return launched("prompt_grad");
 }

@@ -161,3 +161,39 @@ def test_errors_are_loud():
     qkv = torch.zeros(4, 3 * 100, device="cuda", dtype=torch.half)
     with pytest.raises(MvlptError):
         ops.fmha_fwd(qkv, qkv, qkv, 1, 4, 100, 2, 0)  # d != heads*64
+
+
+@pytest.mark.parametrize("B,res,p,dtype", [(3, 224, 16, torch.float16), (2, 224, 32, torch.float16), (2, 224, 14, torch.float16),
+                                           (2, 64, 16, torch.float32)])
+def test_im2col_matches_unfold(B, res, p, dtype):
+    """patch gather of the stride-p conv (clip/model.py:207): the vectorised fp16 path and the scalar one"""
+    from mvlpt_b200 import ops
+    torch.manual_seed(4)
+    img = torch.randn(B, 3, res, res, device="cuda").to(dtype)
+    g = res // p
+    K = 3 * p * p
+    Kp = (K + 7) // 8 * 8
+    patches = torch.full((B * g * g, Kp), 7.0, device="cuda", dtype=torch.half)
+    ops.im2col(img, patches, B, res, res, p, Kp)
+    ref = torch.nn.functional.unfold(img.float(), kernel_size=p, stride=p).transpose(1, 2).reshape(B * g * g, K)
+    assert torch.equal(patches[:, :K].float(), ref.half().float())
+    assert (patches[:, K:] == 0).all()
+
+
+@pytest.mark.parametrize("f16_stream", [False, True])
+def test_prompt_grad_reduces_over_batch_and_clears_rows(f16_stream):
+    from mvlpt_b200 import ops
+    torch.manual_seed(5)
+    B, L, v, d = 37, 21, 4, 768
+    dx = torch.randn(B * L, d, device="cuda")
+    dx16 = dx.half()
+    ref = dx16.float().view(B, L, d)[:, 1:1 + v].sum(0) * 0.25 if f16_stream else dx.view(B, L, d)[:, 1:1 + v].sum(0) * 0.25
+    grad = torch.empty(v, d, device="cuda")
+    ops.prompt_grad(None if f16_stream else dx, dx16, grad, B, L, v, d, 0.25, zero_rows=True)
+    assert _rel(grad, ref) < 1e-5
+    assert (dx16.view(B, L, d)[:, 1:1 + v] == 0).all() and (dx16.view(B, L, d)[:, 0] != 0).any()
+    if not f16_stream:
+        assert (dx.view(B, L, d)[:, 1:1 + v] == 0).all()
+    g2 = torch.empty(v, d, device="cuda")
+    ops.prompt_grad(None if f16_stream else dx, dx16, g2, B, L, v, d, 1.0, zero_rows=False)
+    assert (g2 == 0).all()
