@@ -342,21 +342,34 @@ prompt_grad_kernel(float* __restrict__ dx, __half* __restrict__ dx16, float* __r
     const int c = (blockIdx.x * 16 + cg) * 4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     if (c < d) {
-        for (int b = bl; b < B; b += 16) {
-            const size_t off = ((size_t)b * L + 1 + j) * d + c;
-            float4 t;
-            if (dx) {
-                t = *reinterpret_cast<const float4*>(dx + off);
-            } else {  // fp16 gradient stream
-                const uint2 u = *reinterpret_cast<const uint2*>(dx16 + off);
-                const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
-                const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
-                t = make_float4(lo.x, lo.y, hi.x, hi.y);
+        // 8 rows per round: all loads first (the stores that clear the rows would otherwise fence every next load)
+        for (int b0 = bl; b0 < B; b0 += 16 * 8) {
+            float4 t[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int b = b0 + 16 * k;
+                t[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (b < B) {
+                    const size_t off = ((size_t)b * L + 1 + j) * d + c;
+                    if (dx) {
+                        t[k] = *reinterpret_cast<const float4*>(dx + off);
+                    } else {  // fp16 gradient stream
+                        const uint2 u = *reinterpret_cast<const uint2*>(dx16 + off);
+                        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+                        const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+                        t[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
+                }
             }
-            acc.x += t.x; acc.y += t.y; acc.z += t.z; acc.w += t.w;
-            if (zero_rows) {
-                if (dx) *reinterpret_cast<float4*>(dx + off) = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(0u, 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const int b = b0 + 16 * k;
+                acc.x += t[k].x; acc.y += t[k].y; acc.z += t[k].z; acc.w += t[k].w;
+                if (zero_rows && b < B) {
+                    const size_t off = ((size_t)b * L + 1 + j) * d + c;
+                    if (dx) *reinterpret_cast<float4*>(dx + off) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (dx16) *reinterpret_cast<uint2*>(dx16 + off) = make_uint2(0u, 0u);
+                }
             }
         }
     }

@@ -27,7 +27,7 @@ if [[ $what == *launches* ]]; then
 fi
 if [[ $what == *ncu* ]]; then
   B="python bench.py --mode vpt --steps 1 --warmup 1 --no-cpu-baseline --no-roofline --no-e2e"
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_f16 -s 60 -c 10 -f -o gpurun_out/prof_gemm $B > gpurun_out/ncu_gemm.log 2>&1
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_f16 -s 110 -c 12 -f -o gpurun_out/prof_gemm $B > gpurun_out/ncu_gemm.log 2>&1
   echo "ncu gemm exit $?"
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:fmha_fwd -s 3 -c 2 -f -o gpurun_out/prof_fmha_fwd $B > gpurun_out/ncu_fmha_fwd.log 2>&1
   echo "ncu fmha_fwd exit $?"
