@@ -292,6 +292,10 @@ def ours_arm(a):
                "d2h_bytes_per_step": 8}
 
     flops = flops_step(synth.ARCHS[ARCH], B, a.classes, a.ctx_len, v, n)
+    # rows of the causal text tower behind the last EOT are not computed (they cannot reach any output): the FLOPs
+    # actually executed are reported next to the reference's algorithmic count and are the ones "achieved" uses
+    Lk = int(trainer.model.prompt_learner.kernel_len)
+    flops_exec = flops_step(synth.ARCHS[ARCH], B, a.classes, Lk, v, n)
     peaks = {}
     pk = REPO / "MEASURED_PEAKS.json"
     if pk.exists():
@@ -335,8 +339,12 @@ def ours_arm(a):
             "config": {"workload": workload_name(a), "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": f"{nbuf} distinct input batches rotated; per-step activation working set >> 126 MB L2",
                        "step_tflop_algorithmic": flops / 1e12,
-                       "step_tflops_achieved_per_gpu": flops / (ms_dev * 1e-3) / 1e12,
-                       "step_frac_of_peak": flops / (ms_dev * 1e-3) / 1e12 / tf_peak},
+                       "step_tflop_executed": flops_exec / 1e12,
+                       "text_causal_cut": {"L_t": a.ctx_len, "rows_computed": Lk,
+                                           "note": "rows behind the last EOT cannot influence the EOT rows of a causal "
+                                                   "tower; features and gradients are bit-identical to all L_t rows"},
+                       "step_tflops_achieved_per_gpu": flops_exec / (ms_dev * 1e-3) / 1e12,
+                       "step_frac_of_peak": flops_exec / (ms_dev * 1e-3) / 1e12 / tf_peak},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels,
         }

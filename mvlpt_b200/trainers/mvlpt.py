@@ -224,13 +224,21 @@ class MultitaskVLPromptLearner(nn.Module):
         full = torch.cat([embedding[:, :1], torch.zeros(n_cls, coop_n_ctx, coop_ctx_dim, dtype=dtype),
                           embedding[:, 1 + coop_n_ctx:]], dim=1).float()
         pos = self.class_token_position if coop_n_ctx else "end"
-        self.register_buffer("_emb", E.rearrange_embedding(full, self.name_lens, coop_n_ctx, pos).contiguous(),
-                             persistent=False)
+        emb_full = E.rearrange_embedding(full, self.name_lens, coop_n_ctx, pos)
         slot, ctx_pos = E.build_ctx_maps(self.name_lens, coop_n_ctx, Lt, pos)
-        self.register_buffer("_slot", slot, persistent=False)
-        self.register_buffer("_ctx_pos", ctx_pos, persistent=False)
         eot = tokenized_prompts.argmax(dim=-1)
-        self.register_buffer("_eot_rows", (torch.arange(n_cls) * Lt + eot).to(torch.int32), persistent=False)
+        # Causal cut.  The text tower is causal (clip/model.py:324-330) and only the EOT row of each class is read
+        # (trainers/mvlpt.py:124-128): rows after the last EOT of the class set can influence neither the features nor
+        # any gradient, so the kernels run on the first `kernel_len` rows only.  Bit-for-bit the same features as the
+        # full 77 rows; it is what TRAINER.CUT_CONTEXTLEN (trainers/mvlpt.py:297-300) does to the tokens, applied to
+        # the computation.  MVLPT_TEXT_CAUSAL_CUT=0 keeps every row.
+        self.context_len = Lt
+        self.kernel_len = int(eot.max()) + 1 if os.environ.get("MVLPT_TEXT_CAUSAL_CUT", "1") != "0" else Lt
+        Lk = self.kernel_len
+        self.register_buffer("_emb", emb_full[:, :Lk].contiguous(), persistent=False)
+        self.register_buffer("_slot", slot[:, :Lk].contiguous(), persistent=False)
+        self.register_buffer("_ctx_pos", ctx_pos, persistent=False)
+        self.register_buffer("_eot_rows", (torch.arange(n_cls) * Lk + eot).to(torch.int32), persistent=False)
         self._upt: Optional[UptProjection] = None
 
     # ---- UPT -------------------------------------------------------------------------------------------------
@@ -266,13 +274,17 @@ class MultitaskVLPromptLearner(nn.Module):
             ctx = self.ctx
         if self.class_token_position not in ("end", "middle", "front"):
             raise ValueError
-        C, Lt, d = self._emb.shape
+        C, Lk, d = self._emb.shape
         _require_cuda(self._emb, "forward_coop")
-        out = torch.empty(C, Lt, d, device=self._emb.device, dtype=torch.float32)
-        zero_pos = torch.zeros(Lt, d, device=self._emb.device, dtype=torch.float32)
+        out = torch.empty(C, Lk, d, device=self._emb.device, dtype=torch.float32)
+        zero_pos = torch.zeros(Lk, d, device=self._emb.device, dtype=torch.float32)
         c = None if ctx is None else ctx.detach().contiguous()
-        ops.text_assemble(self._emb, c, self._slot, zero_pos, out, C, Lt, self.coop_n_ctx, d, self.csc)
-        return out.to(self._emb.dtype if ctx is None else ctx.dtype)
+        ops.text_assemble(self._emb, c, self._slot, zero_pos, out, C, Lk, self.coop_n_ctx, d, self.csc)
+        out = out.to(self._emb.dtype if ctx is None else ctx.dtype)
+        if Lk < self.context_len:  # the rows behind the causal cut are the untouched token embeddings (API parity)
+            tail = self.token_suffix[:, Lk - 1 - self.coop_n_ctx:, :].to(out.dtype)
+            out = torch.cat([out, tail], dim=1)
+        return out
 
     def forward_cocoop(self, im_features):
         raise NotImplementedError("CoCoOp branch is outside this build's hot path (SURVEY.md §8f rank 3)")
@@ -344,6 +356,9 @@ class TextEncoder(nn.Module):
         _require_cuda(prompts, "TextEncoder")
         C, Lt, _ = prompts.shape
         eot = tokenized_prompts.argmax(dim=-1).to(prompts.device)
+        if os.environ.get("MVLPT_TEXT_CAUSAL_CUT", "1") != "0":
+            Lt = int(eot.max()) + 1  # rows after the last EOT cannot reach any EOT row through the causal mask
+            prompts = prompts[:, :Lt]
         rows = (torch.arange(C, device=prompts.device) * Lt + eot).to(torch.int32)
         feat = self.tower(prompts.device).forward(prompts.float().contiguous(), None, None, rows, 0, False, train=False)
         return feat.to(self.dtype)

@@ -138,3 +138,26 @@ def test_full_size_properties():
         assert rel_err(g_a[k] + g_b[k], g_full[k]) < 2e-3, k
     for b, w in zip(tower.blocks[:2], w_before):
         assert torch.equal(b.w_qkv, w)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["tiny_coop_end", "tiny_coop_front_csc", "b16_coop_end"])
+def test_causal_cut_of_the_text_tower_changes_nothing(name, monkeypatch):
+    """Rows behind the last EOT cannot reach an EOT row through the causal mask (clip/model.py:324-330): running the text
+    tower on the first max(eot)+1 rows must give the logits and the context gradients of all context_length rows."""
+    from tests.helpers import build_custom_clip, rel_err
+    out = {}
+    for cut in ("1", "0"):
+        monkeypatch.setenv("MVLPT_TEXT_CAUSAL_CUT", cut)
+        model, fx, case, sd, image, pp, upt = build_custom_clip(name, "fp16", device="cuda")
+        pl = model.prompt_learner
+        assert pl.context_len == fx["tokenized_prompts"].shape[1]
+        assert (pl.kernel_len < pl.context_len) == (cut == "1")
+        loss_rows, pred, grads = model.loss_and_grads(image.cuda().half(), fx["label"].cuda(), fx["task"])
+        torch.cuda.synchronize()
+        out[cut] = (model.last_logits(image.shape[0]).float().clone(), {k: v.float().clone() for k, v in grads.items()},
+                    model.prompt_learner.forward_coop().float().clone())
+    assert torch.equal(out["1"][0], out["0"][0]), "logits differ"
+    for k in out["0"][1]:
+        assert rel_err(out["1"][1][k], out["0"][1][k]) < 1e-6, k
+    assert torch.equal(out["1"][2], out["0"][2]), "forward_coop (API parity, full length) differs"
