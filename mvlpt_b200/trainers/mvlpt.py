@@ -476,28 +476,12 @@ class CustomCLIP(nn.Module):
         self._shapes = dict(B=B, C=C, v=0 if vpt is None else vpt.shape[1],
                             n_deep=None if deep is None else deep.shape[0], Lt=pl._emb.shape[1])
         head = self.head(dev)
-        # the text tower does not depend on the images: it runs first, while the batch is still crossing PCIe
+        # the text tower does not depend on the images: it runs first, while the batch is still crossing PCIe.  (Issuing it
+        # on a second stream, to fill the tails of the image tower's persistent kernels, was measured: no gain.)
         if ctx is not None or not (self.cache_text_features and self._txt_cache_valid == (B, C)):
-            sh = self._text_shard(dev)
-            tt = self.text_encoder.tower(dev)
-            if sh is None:
-                txt_feat = tt.forward(pl._emb, ctx, pl._slot, pl._eot_rows, pl.coop_n_ctx, pl.csc, train=self._txt_train)
-            else:
-                c0, c1 = sh["range"]
-                ctx_l = ctx[c0:c1] if (ctx is not None and pl.csc) else ctx
-                if c1 > c0:
-                    local = tt.forward(pl._emb[c0:c1], ctx_l, pl._slot[c0:c1], sh["eot_rows"], pl.coop_n_ctx, pl.csc,
-                                       train=self._txt_train)
-                    sh["send"][:c1 - c0].copy_(local)
-                self.dp.all_gather_into(sh["gathered"], sh["send"])
-                txt_feat = sh["full"]
-                for r, (a, b) in enumerate(sh["ranges"]):  # drop the padding rows of each rank's slab
-                    if b > a:
-                        txt_feat[a:b].copy_(sh["gathered"][r, :b - a])
-            head.normalize_text(txt_feat, B)
-            self._txt_cache_valid = (B, C) if ctx is None else False
+            self._text_features(dev, ctx, B, C)
         if ready is not None:
-            torch.cuda.current_stream().wait_event(ready)
+            torch.cuda.current_stream(dev).wait_event(ready)
         image = image.contiguous()
         if image.dtype not in (torch.float16, torch.float32):
             image = image.float()
@@ -507,6 +491,30 @@ class CustomCLIP(nn.Module):
         if t_dev is not None:
             ops.task_mask(logits, head.buffers(B, C)["ldc"], t_dev, ranges, B, C)
         return logits
+
+    def _text_features(self, dev, ctx, B: int, C: int):
+        """Text tower forward (class-sharded under data parallelism) + L2 normalisation into the head's buffers, on the
+        current stream."""
+        pl = self.prompt_learner
+        head = self.head(dev)
+        sh = self._text_shard(dev)
+        tt = self.text_encoder.tower(dev)
+        if sh is None:
+            txt_feat = tt.forward(pl._emb, ctx, pl._slot, pl._eot_rows, pl.coop_n_ctx, pl.csc, train=self._txt_train)
+        else:
+            c0, c1 = sh["range"]
+            ctx_l = ctx[c0:c1] if (ctx is not None and pl.csc) else ctx
+            if c1 > c0:
+                local = tt.forward(pl._emb[c0:c1], ctx_l, pl._slot[c0:c1], sh["eot_rows"], pl.coop_n_ctx, pl.csc,
+                                   train=self._txt_train)
+                sh["send"][:c1 - c0].copy_(local)
+            self.dp.all_gather_into(sh["gathered"], sh["send"])
+            txt_feat = sh["full"]
+            for r, (a, b) in enumerate(sh["ranges"]):  # drop the padding rows of each rank's slab
+                if b > a:
+                    txt_feat[a:b].copy_(sh["gathered"][r, :b - a])
+        head.normalize_text(txt_feat, B)
+        self._txt_cache_valid = (B, C) if ctx is None else False
 
     def grad_buffer(self) -> torch.Tensor:
         """Flat fp32 gradient buffer over every trainable prompt tensor, in named_parameters() order.  The engine writes
