@@ -1,4 +1,5 @@
 #include "common.cuh"
+#include <stdlib.h>
 
 #include <string.h>
 
@@ -111,3 +112,14 @@ int mvlpt_check_device(int dev) {
 }
 
 }  // extern "C"
+
+namespace mvlpt {
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MVLPT_PDL");
+        on = (e && e[0] == '0') ? 0 : 1;
+    }
+    return on != 0;
+}
+}  // namespace mvlpt

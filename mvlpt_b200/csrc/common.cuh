@@ -49,6 +49,40 @@ int make_tmap(CUtensorMap* out, const void* base, int is_f32, int rank, const ui
               const uint64_t* strides_bytes, const uint32_t* box);
 
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+// Programmatic dependent launch (PDL).  A kernel launched with `launch_pdl` may begin while its predecessor in the
+// stream is still draining: its CTAs are scheduled as soon as the predecessor's CTAs have all started and SM resources
+// free up, run their prologue (barrier init, TMEM allocation, descriptor prefetch) and then block in `pdl_wait()` until
+// the predecessor has completed and its memory is visible.  Every kernel launched this way executes
+// `pdl_launch_dependents(); pdl_wait();` before its first global-memory access.  MVLPT_PDL=0 turns the attribute off.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                              unsigned cluster_x, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[2];
+    unsigned n = 0;
+    if (cluster_x > 1) {
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster_x;
+        at[n].val.clusterDim.y = 1;
+        at[n].val.clusterDim.z = 1;
+        ++n;
+    }
+    if (pdl_enabled()) {
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
+    }
+    cfg.attrs = at;
+    cfg.numAttrs = n;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 int sm_count();
 
 }  // namespace mvlpt

@@ -122,6 +122,8 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -537,7 +539,7 @@ inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const
         attr = smem;
     }
     const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-    fmha_bwd_tc_kernel<<<grid, kFmhaBwdThreads, smem, stream>>>(tq, tq, tdo, tdq, p);
+    MVLPT_CUDA_OK(launch_pdl(fmha_bwd_tc_kernel, dim3(grid), dim3(kFmhaBwdThreads), smem, stream, 1, tq, tq, tdo, tdq, p));
     return launched("fmha_bwd_tc");
 }
 

@@ -344,6 +344,8 @@ fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0) {
         // ============================== TMA producer ==============================
@@ -589,7 +591,7 @@ inline int fmha_fwd2_sm100(const void* qkv, void* out, void* lse, int N, int L, 
         attr = smem;
     }
     const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-    fmha_fwd_tc2_kernel<<<grid, kFmhaFwd2Threads, smem, stream>>>(tq, tkv, to, p);
+    MVLPT_CUDA_OK(launch_pdl(fmha_fwd_tc2_kernel, dim3(grid), dim3(kFmhaFwd2Threads), smem, stream, 1, tq, tkv, to, p));
     return launched("fmha_fwd_tc2");
 }
 

@@ -79,7 +79,8 @@ static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, c
     }
     const int tiles = cdiv(d->M, kGemmBM) * cdiv(d->N, BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
-    gemm_f16_tn_kernel<BN, F32><<<grid, kGemmThreads, smem_bytes, stream>>>(ta, tw, to, tx, ti, d->M, d->N, d->K, ep);
+    MVLPT_CUDA_OK(launch_pdl(gemm_f16_tn_kernel<BN, F32>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, 1, ta, tw, to, tx, ti,
+                             d->M, d->N, d->K, ep));
     return launched("gemm_f16_tn");
 }
 
@@ -157,19 +158,8 @@ static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* 
     }
     const int tiles = cdiv(d->M, 2 * kGemmBM) * cdiv(d->N, 256);
     const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(2 * pairs);
-    cfg.blockDim = dim3(kGemm2Threads);
-    cfg.dynamicSmemBytes = smem_bytes;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    MVLPT_CUDA_OK(cudaLaunchKernelEx(&cfg, gemm_f16_tn_2sm_kernel<F32>, ta, tw, to, tx, ti, d->M, d->N, d->K, ep));
+    MVLPT_CUDA_OK(launch_pdl(gemm_f16_tn_2sm_kernel<F32>, dim3(2 * pairs), dim3(kGemm2Threads), smem_bytes, stream, 2, ta, tw, to,
+                             tx, ti, d->M, d->N, d->K, ep));
     return launched("gemm_f16_tn_2sm");
 }
 

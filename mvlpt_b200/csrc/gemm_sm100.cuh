@@ -142,6 +142,8 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();  // the next kernel of the stream may start its prologue ...
+    pdl_wait();               // ... and this one touches global memory only once its predecessor is complete
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -420,6 +422,8 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     cluster_sync_all();  // barriers of both CTAs are initialised before either touches the other's
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_launch_dependents();  // the next kernel of the stream may start its prologue ...
+    pdl_wait();               // ... and this one touches global memory only once its predecessor is complete
 
     if (warp == 0) {
         // ===================== TMA producer (both CTAs) =====================

@@ -12,6 +12,11 @@ namespace {
 
 constexpr int kMaxV4 = 8;  // d <= 8 * 128
 
+__device__ __forceinline__ void pdl_sync() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 __device__ __forceinline__ float wsum(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -99,6 +104,7 @@ __device__ __forceinline__ void row_affine(Row& r, const float* g, const float* 
 __global__ void ln_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_index,
                               const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
                               int rows, int d, float eps) {
+    pdl_sync();
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
@@ -165,6 +171,7 @@ template <int NV, bool STREAM_F32>
 __global__ void __launch_bounds__(256)
 ln_bwd_fast_kernel(const __half* __restrict__ dy, const float* __restrict__ x, const float* __restrict__ gamma,
                    float* __restrict__ dx_stream, __half* __restrict__ dx16, int rows, float eps, int accumulate) {
+    pdl_sync();
     constexpr int d = NV * 128;
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -236,13 +243,13 @@ template <int NV>
 static void launch_ln_bwd_fast(const void* dy, const void* x, const void* gamma, void* dx_stream, void* dx16, int rows,
                                float eps, int accumulate, cudaStream_t s) {
     if (dx_stream)
-        ln_bwd_fast_kernel<NV, true><<<cdiv(rows, 8), 256, 0, s>>>(static_cast<const __half*>(dy), static_cast<const float*>(x),
-                                                                  static_cast<const float*>(gamma), static_cast<float*>(dx_stream),
-                                                                  static_cast<__half*>(dx16), rows, eps, accumulate);
+        launch_pdl(ln_bwd_fast_kernel<NV, true>, dim3(cdiv(rows, 8)), dim3(256), 0, s, 1, static_cast<const __half*>(dy),
+                   static_cast<const float*>(x), static_cast<const float*>(gamma), static_cast<float*>(dx_stream),
+                   static_cast<__half*>(dx16), rows, eps, accumulate);
     else
-        ln_bwd_fast_kernel<NV, false><<<cdiv(rows, 8), 256, 0, s>>>(static_cast<const __half*>(dy), static_cast<const float*>(x),
-                                                                   static_cast<const float*>(gamma), nullptr,
-                                                                   static_cast<__half*>(dx16), rows, eps, accumulate);
+        launch_pdl(ln_bwd_fast_kernel<NV, false>, dim3(cdiv(rows, 8)), dim3(256), 0, s, 1, static_cast<const __half*>(dy),
+                   static_cast<const float*>(x), static_cast<const float*>(gamma), static_cast<float*>(nullptr),
+                   static_cast<__half*>(dx16), rows, eps, accumulate);
 }
 
 // ---------------------------------------------------------------- im2col for the patch-embedding conv
@@ -459,9 +466,9 @@ int mvlpt_ln_fwd(const void* x, const void* row_index, const void* gamma, const 
     int rc = check_d(d, "mvlpt_ln_fwd");
     if (rc) return rc;
     if ((rc = require_sm100())) return rc;
-    ln_fwd_kernel<<<cdiv(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<const float*>(x), static_cast<const int*>(row_index), static_cast<const float*>(gamma),
-        static_cast<const float*>(beta), static_cast<__half*>(y), rows, d, eps);
+    MVLPT_CUDA_OK(launch_pdl(ln_fwd_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                             static_cast<const float*>(x), static_cast<const int*>(row_index), static_cast<const float*>(gamma),
+                             static_cast<const float*>(beta), static_cast<__half*>(y), rows, d, eps));
     return launched("ln_fwd");
 }
 
