@@ -317,7 +317,7 @@ def ours_arm(a):
                        "gbs": (r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] else None} for k, r in summ.items()}
         if g:
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "gemm_f16_tn_kernel (tcgen05+TMA linear, all launches of the step)",
+            roofline = {"bound": "tensor", "kernel": "gemm_f16_tn_2sm_kernel / gemm_f16_tn_kernel (tcgen05+TMA linear, all launches of the step)",
                         "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
                         "peak_source": peak_src, "launches_per_step": g["launches"] / a.steps,
                         "avg_launch_us": g["ms"] * 1e3 / g["launches"],
