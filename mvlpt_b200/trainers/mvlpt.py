@@ -478,8 +478,11 @@ class CustomCLIP(nn.Module):
         head = self.head(dev)
         # the text tower does not depend on the images: it runs first, while the batch is still crossing PCIe.  (Issuing it
         # on a second stream, to fill the tails of the image tower's persistent kernels, was measured: no gain.)
-        if ctx is not None or not (self.cache_text_features and self._txt_cache_valid == (B, C)):
+        held = getattr(self, "_txt_hold", False) and not train and getattr(self, "_txt_held_for", None) == C
+        if not held and (ctx is not None or not (self.cache_text_features and self._txt_cache_valid == (B, C))):
             self._text_features(dev, ctx, B, C)
+            if getattr(self, "_txt_hold", False) and not train:
+                self._txt_held_for = C
         if ready is not None:
             torch.cuda.current_stream(dev).wait_event(ready)
         image = image.contiguous()
@@ -491,6 +494,12 @@ class CustomCLIP(nn.Module):
         if t_dev is not None:
             ops.task_mask(logits, head.buffers(B, C)["ldc"], t_dev, ranges, B, C)
         return logits
+
+    def hold_text_features(self, on: bool):
+        """While held, the text tower runs at most once more: its features are constant as long as no prompt parameter
+        changes (evaluation, trainers/mvlpt.py:989-1088 recomputes them for every batch)."""
+        self._txt_hold = bool(on)
+        self._txt_held_for = None
 
     def _text_features(self, dev, ctx, B: int, C: int):
         """Text tower forward (class-sharded under data parallelism) + L2 normalisation into the head's buffers, on the
@@ -772,26 +781,77 @@ class MVLPT:
 
     @torch.no_grad()
     def test(self, split=None):
-        """trainers/mvlpt.py:989-1088, reduced to its arithmetic: top-1 accuracy of model_inference over a loader
-        (per task when multi_task).  The ELEVATER metric zoo (mean-per-class, 11-pt mAP) is out of scope."""
+        """trainers/mvlpt.py:989-1088.  Same flow and the same numbers; what differs is where the work happens: the text
+        features are computed once for the whole evaluation (they are constant while no parameter moves), logits stay on
+        the device until the loader is exhausted, and the reference's per-sample Python scatter into per-task evaluators
+        (:1030-1042) is one boolean mask per task.  CoOp-style datasets (cfg.DATASET.COOP) report Dassl's classification
+        accuracy in percent; ELEVATER-style ones the task's own metric (accuracy / mean-per-class / 11point_mAP / roc_auc,
+        `dm._metric_name`, `dm._metric`, else trainers/metrics.py).  Returns the first value of the final `results` dict
+        like the reference; the dicts are kept in `self.last_test_results`."""
+        import numpy as np
+        from . import metrics as MT
         self.set_model_mode("eval")
         split = split or self.cfg.TEST.SPLIT
-        loader = self.val_loader if split == "val" and self.val_loader is not None else self.test_loader
-        correct, total = {}, {}
-        for batch in loader:
-            image, label, tasks_ = self.parse_batch_test(batch)
-            out = self.model_inference(image, task=tasks_)
-            if label.dim() > 1 and label.shape[-1] > 1:
-                label = label.argmax(dim=1)
-            hit = (out.argmax(dim=1) == label).cpu()
-            keys = tasks_.tolist() if tasks_ is not None else [0] * len(hit)
-            for k, h in zip(keys, hit.tolist()):
-                correct[k] = correct.get(k, 0) + int(h)
-                total[k] = total.get(k, 0) + 1
-        per_task = {k: 100.0 * correct[k] / total[k] for k in total}
-        results = {"accuracy": sum(per_task.values()) / max(1, len(per_task))}
-        results.update({f"task{k}/accuracy": v for k, v in per_task.items()})
-        return results
+        if split == "val" and self.val_loader is not None:
+            loader = self.val_loader
+        else:
+            split, loader = "test", self.test_loader
+        coop = bool(self.cfg.DATASET.COOP)
+        outs, labs, tasks = [], [], []
+        self.model.hold_text_features(True)  # constant during evaluation: one text-tower pass for the whole loader
+        try:
+            for batch in loader:
+                image, label, tasks_ = self.parse_batch_test(batch)
+                outs.append(self.model_inference(image, task=tasks_).float())
+                labs.append(label)
+                if tasks_ is not None:
+                    tasks.append(torch.as_tensor(tasks_).reshape(-1).cpu())
+        finally:
+            self.model.hold_text_features(False)
+        out = torch.cat(outs).cpu() if outs else torch.zeros(0, self.num_classes)
+        lab = torch.cat([l.cpu() for l in labs]) if labs else torch.zeros(0, dtype=torch.long)
+        task_ids = torch.cat(tasks) if tasks else None
+
+        def classification_accuracy(o, l):  # Dassl's Classification evaluator: percent of arg-max hits
+            if l.dim() > 1 and l.shape[-1] > 1:
+                l = l.argmax(dim=1)
+            return 100.0 * float((o.argmax(dim=1) == l).float().mean()) if len(l) else 0.0
+
+        def metric_of(name, fn, y_true, y_pred):
+            fn = fn if fn is not None else MT.get_metric(name)
+            if name == "accuracy" and y_true.ndim > 1:
+                y_true = np.argmax(y_true, axis=-1)
+            return float(fn(y_true, y_pred))
+
+        dm = self.dm
+        per_task = {}
+        if self.multi_task and task_ids is not None:
+            for tid in sorted(set(task_ids.tolist())):
+                name = dm._id2task[tid] if hasattr(dm, "_id2task") else tid
+                sel = task_ids == tid
+                o, l = out[sel], lab[sel]
+                if hasattr(dm, "_task_class_idx"):  # evaluate on the task's own classes (:1036-1040, :1052-1054)
+                    c0, c1 = dm._task_class_idx[name]
+                    o = o[:, c0:c1]
+                    l = l[:, c0:c1] if l.dim() > 1 else l - c0
+                if coop:
+                    per_task[name] = classification_accuracy(o, l)
+                else:
+                    mname = dm._metric_name[name]
+                    per_task[name] = metric_of(mname, getattr(dm, "_metric", {}).get(name), l.numpy(), o.numpy())
+        if per_task:
+            key = self.cfg.DATASET.MULTITASK_EVALKEY
+            if key == "average":
+                results = {"average": sum(per_task.values()) / len(per_task)}
+            else:
+                assert key in per_task, key
+                results = {key: per_task[key]}
+        elif coop or not hasattr(dm, "_metric_name"):
+            results = {"accuracy": classification_accuracy(out, lab)}
+        else:
+            results = {dm._metric_name: metric_of(dm._metric_name, getattr(dm, "_metric", None), lab.numpy(), out.numpy())}
+        self.last_test_results = dict(split=split, results=results, per_task=per_task)
+        return list(results.values())[0]
 
     def load_model(self, directory, epoch=None):
         """trainers/mvlpt.py:1090-1125: <dir>/prompt_learner/model-best.pth.tar | model.pth.tar-<epoch>; renames

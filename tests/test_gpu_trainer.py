@@ -78,4 +78,41 @@ def test_eval_path_and_text_feature_cache():
     tr.test_loader = loader
     res = tr.test()
     acc = 100.0 * float((fx["logits"].argmax(-1) == fx["label"]).float().mean())
-    assert abs(res["accuracy"] - acc) < 1e-6
+    assert abs(res - acc) < 1e-6 and tr.last_test_results["results"] == {"accuracy": res}
+
+
+def test_eval_multitask_elevater_metrics_and_held_text_features():
+    """trainers/mvlpt.py:989-1088, ELEVATER branch: per-task class slices, the task's own metric, MULTITASK_EVALKEY;
+    with trainable context the text tower runs once for the whole loader."""
+    from types import SimpleNamespace as NS
+    from mvlpt_b200 import _lib
+    from mvlpt_b200.trainers import metrics as MT
+    tr, fx, case, sd, image, pp, upt = _trainer("tiny_coop_end")
+    C = tr.model.prompt_learner.n_cls
+    half = C // 2
+    B = image.shape[0]
+    tr.multi_task = True
+    tr.cfg.DATASET.COOP = False
+    tr.cfg.DATASET.MULTITASK_EVALKEY = "average"
+    tr.dm._id2task = {0: "a", 1: "b"}
+    tr.dm._task_class_idx = {"a": (0, half), "b": (half, C)}
+    tr.dm._metric_name = {"a": "accuracy", "b": "11point_mAP"}
+    tr.dm._metric = {}
+    task = torch.tensor([i % 2 for i in range(B)])
+    lab = torch.zeros(B, C)
+    for i in range(B):
+        lo, hi = (0, half) if task[i] == 0 else (half, C)
+        lab[i, lo + (int(fx["label"][i]) % (hi - lo))] = 1
+    h = max(1, B // 2)
+    loader = [{0: image[:h], 1: lab[:h], 3: task[:h]}, {0: image[h:], 1: lab[h:], 3: task[h:]}]
+    tr.test_loader = loader
+    tr.model.cache_text_features = True
+    n0 = _lib.launch_count()
+    res = tr.test()
+    with torch.no_grad():
+        logits = tr.model(image.cuda()).float().cpu()
+    want_a = MT.accuracy(lab[task == 0][:, :half].argmax(1).numpy(), logits[task == 0][:, :half].numpy())
+    want_b = MT.map_11_points(lab[task == 1][:, half:].numpy(), logits[task == 1][:, half:].numpy())
+    assert abs(tr.last_test_results["per_task"]["a"] - want_a) < 1e-9
+    assert abs(tr.last_test_results["per_task"]["b"] - want_b) < 1e-9
+    assert abs(res - (want_a + want_b) / 2) < 1e-9
