@@ -98,7 +98,9 @@ static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* 
     // operand-ring depth / output-ring slots out of the 227 KB: deep operand ring for plain epilogues, deep slab ring
     // when the epilogue has a TMA-loaded input or a second output
     const int per = ep.has_aux_out ? 2 : 1;
-    int stages = (ep.has_in || ep.has_aux_out) ? 4 : 6;
+    // measured (tools/gpu_bench_kernels.py, MVLPT_GEMM2_STAGES sweep): the fp32 residual epilogue is best with 5 operand
+    // stages + 4 slabs, the QuickGELU ones with 4 + 6, plain ones with 6 + 2
+    int stages = (ep.has_in || ep.has_aux_out) ? ((F32 && !ep.has_aux_out) ? 5 : 4) : 6;
     static int forced = -1;
     if (forced < 0) {
         const char* e = getenv("MVLPT_GEMM2_STAGES");
