@@ -98,7 +98,7 @@ def synth_clip_state_dict(arch: str | dict, seed: int = 0) -> "OrderedDict[str, 
 
 
 def synth_prompt_params(arch: str | dict, coop_n_ctx: int, vpt_n_ctx: int, vpt_deep: bool, csc_classes: int = 0,
-                        project_dim: int = 0, seed: int = 0) -> dict:
+                        project_dim: int = 0, seed: int = 0, cocoop_n_ctx: int = 0) -> dict:
     """Trainable prompt tensors under the reference's prompt_learner key names (trainers/mvlpt.py:169-257).
 
     Values are fp16-representable (the reference creates them in CLIP's dtype, trainers/mvlpt.py:151,188-197,222-225).
@@ -117,6 +117,13 @@ def synth_prompt_params(arch: str | dict, coop_n_ctx: int, vpt_n_ctx: int, vpt_d
     if coop_n_ctx:
         shape = (csc_classes, coop_n_ctx, tw) if csc_classes else (coop_n_ctx, tw)
         out["ctx"] = _normal("ctx", seed, shape, 0.02, fp16=True)
+    if cocoop_n_ctx:  # trainers/mvlpt.py:260-290: instance-conditioned context + meta network (e -> e/16 -> d_t)
+        e = a["embed_dim"]
+        out["cocoop_ctx"] = _normal("cocoop_ctx", seed, (cocoop_n_ctx, tw), 0.02, fp16=True)
+        out["meta_net.linear1.weight"] = _normal("meta_net.linear1.weight", seed, (e // 16, e), e ** -0.5, fp16=True)
+        out["meta_net.linear1.bias"] = _normal("meta_net.linear1.bias", seed, (e // 16,), 0.02, fp16=True)
+        out["meta_net.linear2.weight"] = _normal("meta_net.linear2.weight", seed, (tw, e // 16), (e // 16) ** -0.5, fp16=True)
+        out["meta_net.linear2.bias"] = _normal("meta_net.linear2.bias", seed, (tw,), 0.02, fp16=True)
     if project_dim and coop_n_ctx and vpt_n_ctx:
         pd = project_dim
         for nm, (i, o) in {"mvlpt_proj_ctx_coop_pre": (tw, pd), "mvlpt_proj_ctx_coop_post": (pd, tw),

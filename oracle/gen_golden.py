@@ -73,7 +73,7 @@ def make_cfg(case) -> NS:
                             DEEP=case.get("vpt_deep", False)),
                      COOP=NS(N_CTX=case.get("coop_n_ctx", 0), CTX_INIT="", CSC=case.get("csc", False),
                              CLASS_TOKEN_POSITION=case.get("position", "end")),
-                     COCOOP=NS(N_CTX=0, CTX_INIT="", PREC="fp16")),
+                     COCOOP=NS(N_CTX=case.get("cocoop_n_ctx", 0), CTX_INIT="", PREC="fp32")),
             CUT_CONTEXTLEN=case.get("cut", False), ACT_CKPT=1),
         INPUT=NS(SIZE=(res, res)),
         DATASET=NS(MULTITASK_LABEL_PERTASK=case.get("task_mask", False)),
@@ -96,6 +96,8 @@ CASES = [
     dict(name="tiny_upt_identity", arch="tiny", coop_n_ctx=4, vpt_n_ctx=4, vpt_deep=True, B=3, C=5),
     dict(name="tiny_upt_transformer", arch="tiny", coop_n_ctx=4, vpt_n_ctx=4, vpt_deep=True, position="middle",
          cut=True, project_method="transformer", project_dim=32, B=3, C=5),
+    dict(name="tiny_cocoop", arch="tiny", cocoop_n_ctx=4, B=3, C=5),
+    dict(name="tiny_cocoop_vpt_deep", arch="tiny", cocoop_n_ctx=4, vpt_n_ctx=3, vpt_deep=True, B=2, C=6),
     dict(name="b16_coop_end", arch="ViT-B/16", coop_n_ctx=16, B=2, C=10),
     dict(name="b16_vpt_deep", arch="ViT-B/16", vpt_n_ctx=8, vpt_deep=True, B=2, C=10),
     dict(name="b16_upt_transformer", arch="ViT-B/16", coop_n_ctx=16, vpt_n_ctx=8, vpt_deep=True, position="middle",
@@ -138,7 +140,7 @@ def run_case(case, out_dir: Path):
     pp = synth.synth_prompt_params(case["arch"], case.get("coop_n_ctx", 0), case.get("vpt_n_ctx", 0),
                                    case.get("vpt_deep", False), csc_classes=C if case.get("csc") else 0,
                                    project_dim=case.get("project_dim", 0) if case.get("project_method") == "transformer" else 0,
-                                   seed=0)
+                                   seed=0, cocoop_n_ctx=case.get("cocoop_n_ctx", 0))
     missing, unexpected = pl.load_state_dict(pp, strict=False)
     assert not unexpected, unexpected
     assert all(k in ("token_prefix", "token_suffix") for k in missing), missing
@@ -185,9 +187,13 @@ def run_case(case, out_dir: Path):
             ctx, vpt, vpt_deep = pl.forward_mvlpt_proj(torch.float32)
             fix["proj_ctx"], fix["proj_vpt"], fix["proj_vpt_deep"] = ctx, vpt, vpt_deep
             fix["image_features"] = model.image_encoder(image, vpt, vpt_deep)
-            prompts = pl.forward_coop(ctx)
-            fix["prompts"] = prompts
-            fix["text_features"] = model.text_encoder(prompts, tok)
+            if not case.get("cocoop_n_ctx"):
+                prompts = pl.forward_coop(ctx)
+                fix["prompts"] = prompts
+                fix["text_features"] = model.text_encoder(prompts, tok)
+            else:
+                imf = fix["image_features"] / fix["image_features"].norm(dim=-1, keepdim=True)
+                fix["cocoop_prompts"] = pl.forward_cocoop(imf)
     # margins for the argmax check
     top2 = logits.detach().topk(2, dim=-1).values
     fix["top2_margin"] = (top2[:, 0] - top2[:, 1]).clone()

@@ -232,16 +232,42 @@ def sgd_step(params: List[Tensor], grads: List[Tensor], bufs: List[Optional[Tens
 
 
 # ----------------------------------------------------------------------------------------------- whole model
+def cocoop_logits(img_f: Tensor, sd: Dict[str, Tensor], pp: Dict[str, Tensor], embedding: Tensor, eot_index: Tensor,
+                  n_ctx: int) -> Tensor:
+    """CoCoOp branch, trainers/mvlpt.py:348-374 (forward_cocoop) + :556-571: the meta network maps each normalised image
+    feature to a bias that shifts every context vector; every image gets its own set of class prompts, hence its own
+    text features; logits[b, c] = exp(logit_scale) * <img_b, txt_{b,c}>."""
+    img_n = img_f / img_f.norm(dim=-1, keepdim=True)
+    h1 = torch.relu(img_n @ pp["meta_net.linear1.weight"].t().to(img_n.dtype) + pp["meta_net.linear1.bias"].to(img_n.dtype))
+    bias = h1 @ pp["meta_net.linear2.weight"].t().to(img_n.dtype) + pp["meta_net.linear2.bias"].to(img_n.dtype)
+    ctx_shifted = pp["cocoop_ctx"].to(img_n.dtype).unsqueeze(0) + bias.unsqueeze(1)  # [B, n, d_t]
+    scale = sd["logit_scale"].exp()
+    rows = []
+    for b in range(img_f.shape[0]):
+        prompts = coop_prompts(embedding, ctx_shifted[b], (), n_ctx, "end")  # construct_prompts(ctx_i, prefix, suffix)
+        txt = text_tower(prompts, eot_index, sd)
+        txt = txt / txt.norm(dim=-1, keepdim=True)
+        rows.append(scale * img_n[b] @ txt.t())
+    return torch.stack(rows)
+
+
 def custom_clip_forward(image: Tensor, sd: Dict[str, Tensor], pp: Dict[str, Tensor], embedding: Tensor,
                         eot_index: Tensor, name_lens: Sequence[int], n_ctx: int, v: int, position: str = "end",
                         upt: bool = False, task: Optional[Tensor] = None,
-                        task_ranges: Optional[Tensor] = None) -> Tensor:
-    """trainers/mvlpt.py:540-583 (CoCoOp branch excluded): projection -> image tower -> prompt assembly ->
-    text tower -> cosine logits."""
+                        task_ranges: Optional[Tensor] = None, cocoop_n_ctx: int = 0) -> Tensor:
+    """trainers/mvlpt.py:540-583: projection -> image tower -> prompt assembly -> text tower -> cosine logits
+    (or, with COCOOP.N_CTX > 0, the instance-conditioned branch)."""
     ctx, vpt, vpt_deep = pp.get("ctx"), pp.get("vpt_embeddings"), pp.get("vpt_embeddings_deep")
     if upt and ctx is not None and vpt is not None:
         ctx, vpt, vpt_deep = upt_project(pp, n_ctx, v, dtype=image.dtype)
     img_f = image_tower(image, sd, vpt, vpt_deep)
+    if cocoop_n_ctx:
+        logits = cocoop_logits(img_f, sd, pp, embedding.to(image.dtype), eot_index, cocoop_n_ctx)
+        if task is not None and task_ranges is not None:  # :573-581
+            idx = torch.arange(logits.shape[1])
+            lo, hi = task_ranges[task, 0].unsqueeze(-1), task_ranges[task, 1].unsqueeze(-1)
+            logits = logits * ((idx >= lo).float() * (idx < hi).float())
+        return logits
     prompts = coop_prompts(embedding.to(image.dtype), ctx, name_lens, n_ctx, position)
     txt_f = text_tower(prompts, eot_index, sd)
     return logit_head(img_f, txt_f, sd["logit_scale"], task, task_ranges)

@@ -26,7 +26,8 @@ def case_inputs(name: str):
     upt = case.get("project_method") == "transformer"
     pp = synth.synth_prompt_params(case["arch"], case.get("coop_n_ctx", 0), case.get("vpt_n_ctx", 0),
                                    case.get("vpt_deep", False), csc_classes=case["C"] if case.get("csc") else 0,
-                                   project_dim=case.get("project_dim", 0) if upt else 0, seed=0)
+                                   project_dim=case.get("project_dim", 0) if upt else 0, seed=0,
+                                   cocoop_n_ctx=case.get("cocoop_n_ctx", 0))
     return fx, case, arch, sd, image, pp, upt
 
 
@@ -47,7 +48,7 @@ def make_cfg(case, prec="fp16"):
                             DEEP=case.get("vpt_deep", False)),
                      COOP=NS(N_CTX=case.get("coop_n_ctx", 0), CTX_INIT="", CSC=case.get("csc", False),
                              CLASS_TOKEN_POSITION=case.get("position", "end")),
-                     COCOOP=NS(N_CTX=0, CTX_INIT="", PREC="fp16")),
+                     COCOOP=NS(N_CTX=case.get("cocoop_n_ctx", 0), CTX_INIT="", PREC="fp16")),
             CUT_CONTEXTLEN=case.get("cut", False), ACT_CKPT=1),
         INPUT=NS(SIZE=(res, res)),
         DATASET=NS(MULTITASK_LABEL_PERTASK=case.get("task_mask", False)),
@@ -81,4 +82,4 @@ def oracle_kwargs(fx, case, sd, upt):
     emb = sd["token_embedding.weight"][fx["tokenized_prompts"]]
     return dict(embedding=emb, eot_index=fx["eot_index"], name_lens=fx["name_lens"], n_ctx=case.get("coop_n_ctx", 0),
                 v=case.get("vpt_n_ctx", 0), position=case.get("position", "end"), upt=upt, task=fx["task"],
-                task_ranges=fx["task_ranges"])
+                task_ranges=fx["task_ranges"], cocoop_n_ctx=case.get("cocoop_n_ctx", 0))
