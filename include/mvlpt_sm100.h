@@ -195,6 +195,34 @@ int mvlpt_upt_fwd(const mvlpt_upt_desc* d, const void* const* params, void* work
 int mvlpt_upt_bwd(const mvlpt_upt_desc* d, const void* const* params, void* workspace, size_t ws_bytes,
                   const void* d_ctx_out, const void* d_vpt_out, void* const* grads, mvlpt_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * CoCoOp branch (trainers/mvlpt.py:260-290 meta_net, :348-374 forward_cocoop, :556-571 per-image text features).
+ * The text tower itself runs the usual kernels on B*C sequences; these are the pieces around it (fp32 arithmetic;
+ * parameters fp16 or fp32 by param_f16 / ctx_f16).
+ * mvlpt_metanet_fwd: h1[B,H] = relu(imf . W1^T + b1), bias[B,dt] = h1 . W2^T + b2   (imf = L2-normalised image features)
+ * mvlpt_metanet_bwd: from d_bias[B,dt]: dW1[H,e], db1[H], dW2[dt,H], db2[dt] (overwritten) and
+ *   d_imf[B,e] += d_imf_scale * d(loss)/d(imf); d_h1_ws = fp32 [B,H] scratch.
+ * mvlpt_cocoop_assemble: x0[(b,c),t] = (slot[c,t] >= 0 ? ctx[slot] + bias[b] : emb[c,t]) + pos[t]
+ *   (construct_prompts with the instance-shifted context, :362-372, fused with `+ positional_embedding`, :107).
+ * mvlpt_pair_logits_fwd/bwd: logits[b,c] = scale * <img[b], txt[b*C+c]> (:566-569) and its gradients
+ *   d_txt[(b,c)] = scale * dz[b,c] * img[b], d_img[b] = scale * sum_c dz[b,c] * txt[(b,c)]  (dz fp16 [B, ldc]).
+ * mvlpt_cocoop_ctx_grad: d_ctx[j] = inv_scale * sum_{b,c} dx[(b,c), ctx_pos[c,j]] and
+ *   d_bias[b] = inv_scale * sum_{c,j} dx[(b,c), ctx_pos[c,j]]; dx fp16 [B*C*Lk, d]; part_ws = fp32 [B, n_ctx, d] scratch.
+ * ------------------------------------------------------------------------------------------------ */
+int mvlpt_metanet_fwd(const void* imf, const void* W1, const void* b1, const void* W2, const void* b2, int param_f16,
+                      void* h1, void* bias, int B, int e, int H, int dt, mvlpt_stream_t stream);
+int mvlpt_metanet_bwd(const void* d_bias, const void* imf, const void* h1, const void* W1, const void* W2, int param_f16,
+                      void* d_h1_ws, void* dW1, void* db1, void* dW2, void* db2, void* d_imf, float d_imf_scale, int B, int e,
+                      int H, int dt, mvlpt_stream_t stream);
+int mvlpt_cocoop_assemble(const void* emb, const void* ctx, int ctx_f16, const void* bias, const void* slot, const void* pos,
+                          void* x0, int B, int C, int Lk, int d, mvlpt_stream_t stream);
+int mvlpt_pair_logits_fwd(const void* img, const void* txt, float scale, void* logits, int ldc, int B, int C, int e,
+                          mvlpt_stream_t stream);
+int mvlpt_pair_logits_bwd(const void* dz16, int ldc, const void* img, const void* txt, float scale, void* d_txt, void* d_img,
+                          int B, int C, int e, mvlpt_stream_t stream);
+int mvlpt_cocoop_ctx_grad(const void* dx16, const void* ctx_pos, void* part_ws, void* d_ctx, void* d_bias, int B, int C, int Lk,
+                          int n_ctx, int d, float inv_scale, mvlpt_stream_t stream);
+
 /* cudaMemsetAsync(p, 0, bytes) on the stream. */
 int mvlpt_zero(void* p, size_t bytes, mvlpt_stream_t stream);
 

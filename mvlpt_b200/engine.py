@@ -261,28 +261,40 @@ class TextTower:
                 eot_rows: torch.Tensor, n_ctx: int, csc: bool, train: bool) -> torch.Tensor:
         """emb fp32 [C,Lt,d]; ctx [n,d] | [C,n,d] | None; slot int32 [C,Lt]; eot_rows int32 [C] = c*Lt + eot(c)."""
         C, Lt, d = emb.shape
-        bf = self.buffers(C, Lt, train)
+        return self.forward_assembled(C, Lt, eot_rows, train,
+                                      lambda x0: ops.text_assemble(emb, ctx, slot, self.pos, x0, C, Lt, n_ctx, d, csc))
+
+    def forward_assembled(self, N: int, Lt: int, eot_rows: torch.Tensor, train: bool, assemble) -> torch.Tensor:
+        """N sequences of Lt rows; `assemble(x0)` writes the tower input (prompt rows + positional embedding) into the
+        fp32 buffer x0 [N*Lt, d] (CoOp: one sequence per class; CoCoOp: one per (image, class))."""
+        d = self.d
+        bf = self.buffers(N, Lt, train)
         a: TowerBuffers = bf["act"]
-        ops.text_assemble(emb, ctx, slot, self.pos, a.x_in(0), C, Lt, n_ctx, d, csc)
+        assemble(a.x_in(0))
         for l in range(self.layers):
             block_forward(self.blocks[l], a, l, causal=True)
         bf["final"] = a.x_out(self.layers - 1)
-        ops.ln_fwd(bf["final"], self.ln_g, self.ln_b, bf["pooled"], C, d, row_index=eot_rows)
+        ops.ln_fwd(bf["final"], self.ln_g, self.ln_b, bf["pooled"], N, d, row_index=eot_rows)
         ops.gemm(bf["pooled"], self.proj_t, bf["feat"])
         return bf["feat"]
 
-    def backward(self, dfeat16: torch.Tensor, C: int, Lt: int, eot_rows: torch.Tensor, ctx_pos: torch.Tensor,
-                 n_ctx: int, csc: bool, grad_ctx: torch.Tensor, inv_scale: float):
-        bf = self.buffers(C, Lt, True)
+    def backward_to_input(self, dfeat16: torch.Tensor, N: int, Lt: int, eot_rows: torch.Tensor) -> torch.Tensor:
+        """dfeat16 fp16 [N,e] (scaled) -> the gradient w.r.t. the tower input, fp16 (or fp32) [N*Lt, d], scaled."""
+        bf = self.buffers(N, Lt, True)
         a: TowerBuffers = bf["act"]
         ops.gemm(dfeat16, self.proj, bf["dpool"])
         if a.dx is not None:
             ops.zero(a.dx)
         ops.zero(a.dx16)
-        ops.ln_bwd(bf["dpool"], bf["final"], self.ln_g, a.dx, a.dx16, C, self.d, accumulate=False, row_index=eot_rows)
+        ops.ln_bwd(bf["dpool"], bf["final"], self.ln_g, a.dx, a.dx16, N, self.d, accumulate=False, row_index=eot_rows)
         for l in reversed(range(self.layers)):
             block_backward(self.blocks[l], a, l, causal=True)
-        ops.ctx_grad(a.dx if a.dx is not None else a.dx16, ctx_pos, grad_ctx, C, Lt, n_ctx, self.d, csc, inv_scale)
+        return a.dx if a.dx is not None else a.dx16
+
+    def backward(self, dfeat16: torch.Tensor, C: int, Lt: int, eot_rows: torch.Tensor, ctx_pos: torch.Tensor,
+                 n_ctx: int, csc: bool, grad_ctx: torch.Tensor, inv_scale: float):
+        dx0 = self.backward_to_input(dfeat16, C, Lt, eot_rows)
+        ops.ctx_grad(dx0, ctx_pos, grad_ctx, C, Lt, n_ctx, self.d, csc, inv_scale)
 
 
 class LogitHead:

@@ -199,3 +199,46 @@ def sgd(p, buf, g, lr, momentum, wd, first_step):
 
 def zero(t):
     check(_lib.lib().mvlpt_zero(_p(t), t.numel() * t.element_size(), _stream()), "mvlpt_zero")
+
+
+# ---- CoCoOp branch (include/mvlpt_sm100.h: mvlpt_metanet_*, mvlpt_cocoop_*, mvlpt_pair_logits_*) ---------------------
+def _pf16(*ts):
+    dt = {t.dtype for t in ts}
+    if dt == {torch.float16}:
+        return 1
+    if dt == {torch.float32}:
+        return 0
+    raise _lib.MvlptError(f"meta-net parameters must be all fp16 or all fp32, got {dt}")
+
+
+def metanet_fwd(imf, W1, b1, W2, b2, h1, bias):
+    B, e = imf.shape
+    check(_lib.lib().mvlpt_metanet_fwd(_p(imf), _p(W1), _p(b1), _p(W2), _p(b2), _pf16(W1, b1, W2, b2), _p(h1), _p(bias), B, e,
+                                       W1.shape[0], W2.shape[0], _stream()), "mvlpt_metanet_fwd")
+
+
+def metanet_bwd(d_bias, imf, h1, W1, W2, d_h1_ws, dW1, db1, dW2, db2, d_imf, d_imf_scale):
+    B, e = imf.shape
+    check(_lib.lib().mvlpt_metanet_bwd(_p(d_bias), _p(imf), _p(h1), _p(W1), _p(W2), _pf16(W1, W2), _p(d_h1_ws), _p(dW1), _p(db1),
+                                       _p(dW2), _p(db2), _p(d_imf), float(d_imf_scale), B, e, W1.shape[0], W2.shape[0],
+                                       _stream()), "mvlpt_metanet_bwd")
+
+
+def cocoop_assemble(emb, ctx, bias, slot, pos, x0, B, C, Lk, d):
+    check(_lib.lib().mvlpt_cocoop_assemble(_p(emb), _p(ctx), int(ctx.dtype == torch.float16), _p(bias), _p(slot), _p(pos), _p(x0),
+                                           B, C, Lk, d, _stream()), "mvlpt_cocoop_assemble")
+
+
+def pair_logits_fwd(img, txt, scale, logits, ldc, B, C, e):
+    check(_lib.lib().mvlpt_pair_logits_fwd(_p(img), _p(txt), float(scale), _p(logits), ldc, B, C, e, _stream()),
+          "mvlpt_pair_logits_fwd")
+
+
+def pair_logits_bwd(dz16, ldc, img, txt, scale, d_txt, d_img, B, C, e):
+    check(_lib.lib().mvlpt_pair_logits_bwd(_p(dz16), ldc, _p(img), _p(txt), float(scale), _p(d_txt), _p(d_img), B, C, e,
+                                           _stream()), "mvlpt_pair_logits_bwd")
+
+
+def cocoop_ctx_grad(dx16, ctx_pos, part_ws, d_ctx, d_bias, B, C, Lk, n_ctx, d, inv_scale):
+    check(_lib.lib().mvlpt_cocoop_ctx_grad(_p(dx16), _p(ctx_pos), _p(part_ws), _p(d_ctx), _p(d_bias), B, C, Lk, n_ctx, d,
+                                           float(inv_scale), _stream()), "mvlpt_cocoop_ctx_grad")

@@ -109,9 +109,9 @@ class MultitaskVLPromptLearner(nn.Module):
         T = cfg.TRAINER.MVLPT
         n_cls = len(classnames)
         coop_n_ctx, cocoop_n_ctx, vpt_n_ctx = T.COOP.N_CTX, T.COCOOP.N_CTX, T.VPT.N_CTX
-        if cocoop_n_ctx != 0:
-            raise NotImplementedError("CoCoOp (trainers/mvlpt.py:260-290,348-374) is outside this build's hot path "
-                                      "(SURVEY.md §8f rank 3)")
+        if cocoop_n_ctx != 0 and coop_n_ctx != 0:
+            raise NotImplementedError("COOP.N_CTX and COCOOP.N_CTX together: the reference's own token_suffix then no "
+                                      "longer matches forward_coop (trainers/mvlpt.py:312-315); not supported")
         dtype = clip_model.dtype
         coop_ctx_dim = clip_model.ln_final.weight.shape[0]
         vpt_ctx_dim = clip_model.visual.conv1.weight.shape[0]
@@ -183,8 +183,30 @@ class MultitaskVLPromptLearner(nn.Module):
                 raise AttributeError("module 'torch.nn' has no attribute 'GeLU'")
             else:
                 raise ValueError(f"unknown PROJECT_METHOD {method!r}")
+        # CoCoOp (trainers/mvlpt.py:260-290): instance-conditioned context = cocoop_ctx + meta_net(image feature)
         self.cocoop_ctx = None
         self.meta_net = None
+        if cocoop_n_ctx != 0:
+            if T.COCOOP.CTX_INIT:
+                init = T.COCOOP.CTX_INIT.replace("_", " ")
+                cocoop_n_ctx = len(init.split(" "))
+                with torch.no_grad():
+                    emb = clip_model.token_embedding(tokenize(init)).type(dtype)
+                ctx_vectors = emb[0, 1:1 + cocoop_n_ctx, :].clone()
+                prompt_prefix = init
+            else:
+                ctx_vectors = torch.empty(cocoop_n_ctx, coop_ctx_dim, dtype=dtype)
+                nn.init.normal_(ctx_vectors, std=0.02)
+                prompt_prefix = " ".join(["X"] * cocoop_n_ctx)
+            self.cocoop_ctx = nn.Parameter(ctx_vectors)
+            vis_dim = clip_model.visual.output_dim
+            self.meta_net = nn.Sequential(OrderedDict([
+                ("linear1", nn.Linear(vis_dim, vis_dim // 16)),
+                ("relu", nn.ReLU(inplace=True)),
+                ("linear2", nn.Linear(vis_dim // 16, coop_ctx_dim)),
+            ]))
+            if T.COCOOP.PREC == "fp16":
+                self.meta_net.half()
 
         if prompt_prefix is None:
             raise ValueError("at least one of VPT.N_CTX / COOP.N_CTX must be non-zero")
@@ -207,9 +229,12 @@ class MultitaskVLPromptLearner(nn.Module):
                 tokenized_prompts = tokenized_prompts[:, :min(clip_model.context_length, used)]
         with torch.no_grad():
             embedding = clip_model.token_embedding(tokenized_prompts).type(dtype)
+        # rows 1..n_text of every prompt are the learned context (CoOp's, or CoCoOp's instance-shifted one, :312-315)
+        n_text = cocoop_n_ctx if cocoop_n_ctx != 0 else coop_n_ctx
+        self.text_n_ctx = n_text
         # saved with the checkpoint, ignored on load (trainers/mvlpt.py:309-316, 1117-1121)
         self.register_buffer("token_prefix", embedding[:, :1, :].clone())
-        self.register_buffer("token_suffix", embedding[:, 1 + coop_n_ctx:, :].clone())
+        self.register_buffer("token_suffix", embedding[:, 1 + n_text:, :].clone())
 
         self.n_cls = n_cls
         self.vpt_n_ctx = vpt_n_ctx
@@ -221,11 +246,11 @@ class MultitaskVLPromptLearner(nn.Module):
         self.csc = bool(self.ctx is not None and self.ctx.dim() == 3)
         # kernel-side view of the prompt layout (built once; replaces the per-class cat loop of :472-510)
         Lt = tokenized_prompts.shape[1]
-        full = torch.cat([embedding[:, :1], torch.zeros(n_cls, coop_n_ctx, coop_ctx_dim, dtype=dtype),
-                          embedding[:, 1 + coop_n_ctx:]], dim=1).float()
-        pos = self.class_token_position if coop_n_ctx else "end"
-        emb_full = E.rearrange_embedding(full, self.name_lens, coop_n_ctx, pos)
-        slot, ctx_pos = E.build_ctx_maps(self.name_lens, coop_n_ctx, Lt, pos)
+        full = torch.cat([embedding[:, :1], torch.zeros(n_cls, n_text, coop_ctx_dim, dtype=dtype),
+                          embedding[:, 1 + n_text:]], dim=1).float()
+        pos = self.class_token_position if coop_n_ctx else "end"  # forward_cocoop always appends the class name (:369)
+        emb_full = E.rearrange_embedding(full, self.name_lens, n_text, pos)
+        slot, ctx_pos = E.build_ctx_maps(self.name_lens, n_text, Lt, pos)
         eot = tokenized_prompts.argmax(dim=-1)
         # Causal cut.  The text tower is causal (clip/model.py:324-330) and only the EOT row of each class is read
         # (trainers/mvlpt.py:124-128): rows after the last EOT of the class set can influence neither the features nor
@@ -282,12 +307,35 @@ class MultitaskVLPromptLearner(nn.Module):
         ops.text_assemble(self._emb, c, self._slot, zero_pos, out, C, Lk, self.coop_n_ctx, d, self.csc)
         out = out.to(self._emb.dtype if ctx is None else ctx.dtype)
         if Lk < self.context_len:  # the rows behind the causal cut are the untouched token embeddings (API parity)
-            tail = self.token_suffix[:, Lk - 1 - self.coop_n_ctx:, :].to(out.dtype)
+            tail = self.token_suffix[:, Lk - 1 - self.text_n_ctx:, :].to(out.dtype)
             out = torch.cat([out, tail], dim=1)
         return out
 
+    def meta_params(self):
+        m = self.meta_net
+        return m.linear1.weight, m.linear1.bias, m.linear2.weight, m.linear2.bias
+
     def forward_cocoop(self, im_features):
-        raise NotImplementedError("CoCoOp branch is outside this build's hot path (SURVEY.md §8f rank 3)")
+        """trainers/mvlpt.py:348-374: prompts [B, n_cls, L_t, d_t] with the context shifted by meta_net(im_features)
+        (without positional embedding).  API parity; the fused path assembles straight into the text tower's input."""
+        if self.cocoop_ctx is None:
+            return torch.cat([self.token_prefix, self.token_suffix], dim=1)
+        _require_cuda(self._emb, "forward_cocoop")
+        dev = self._emb.device
+        B, e = im_features.shape
+        C, Lk, d = self._emb.shape
+        W1, b1, W2, b2 = [t.detach().contiguous() for t in self.meta_params()]
+        h1 = torch.empty(B, W1.shape[0], device=dev, dtype=torch.float32)
+        bias = torch.empty(B, d, device=dev, dtype=torch.float32)
+        ops.metanet_fwd(im_features.detach().float().contiguous(), W1, b1, W2, b2, h1, bias)
+        out = torch.empty(B, C, Lk, d, device=dev, dtype=torch.float32)
+        zero_pos = torch.zeros(Lk, d, device=dev, dtype=torch.float32)
+        ops.cocoop_assemble(self._emb, self.cocoop_ctx.detach().contiguous(), bias, self._slot, zero_pos, out, B, C, Lk, d)
+        out = out.to(self.cocoop_ctx.dtype)
+        if Lk < self.context_len:
+            tail = self.token_suffix[:, Lk - 1 - self.text_n_ctx:, :].to(out.dtype)
+            out = torch.cat([out, tail.unsqueeze(0).expand(B, -1, -1, -1)], dim=2)
+        return out
 
     def construct_prompts(self, ctx, prefix, suffix, label=None):
         """trainers/mvlpt.py:327-346 (API parity)."""
@@ -472,12 +520,14 @@ class CustomCLIP(nn.Module):
         cont = lambda t: None if t is None else t.detach().contiguous()
         ctx, vpt, deep = cont(ctx), cont(vpt), cont(deep)
         self._img_train = bool(train and vpt is not None)
-        self._txt_train = bool(train and ctx is not None)
+        self._txt_train = bool(train and (ctx is not None or pl.cocoop_ctx is not None))
         self._shapes = dict(B=B, C=C, v=0 if vpt is None else vpt.shape[1],
                             n_deep=None if deep is None else deep.shape[0], Lt=pl._emb.shape[1])
         head = self.head(dev)
         # the text tower does not depend on the images: it runs first, while the batch is still crossing PCIe.  (Issuing it
         # on a second stream, to fill the tails of the image tower's persistent kernels, was measured: no gain.)
+        if pl.cocoop_ctx is not None:
+            return self._forward_cocoop(image, ready, vpt, deep, task, train)
         held = getattr(self, "_txt_hold", False) and not train and getattr(self, "_txt_held_for", None) == C
         if not held and (ctx is not None or not (self.cache_text_features and self._txt_cache_valid == (B, C))):
             self._text_features(dev, ctx, B, C)
@@ -494,6 +544,90 @@ class CustomCLIP(nn.Module):
         if t_dev is not None:
             ops.task_mask(logits, head.buffers(B, C)["ldc"], t_dev, ranges, B, C)
         return logits
+
+    # ---- CoCoOp branch (trainers/mvlpt.py:556-571) -------------------------------------------------------------------
+    def _cocoop_buffers(self, dev, B: int, C: int):
+        pl = self.prompt_learner
+        e, d, n = self._embed_dim, pl._emb.shape[2], pl.text_n_ctx
+        H = pl.meta_net.linear1.weight.shape[0]
+        key = (B, C, str(dev))
+        if getattr(self, "_cc_key", None) != key:
+            z = lambda *sz, dt=torch.float32: torch.zeros(*sz, device=dev, dtype=dt)
+            Lk = pl._emb.shape[1]
+            bc = torch.arange(B * C, device=dev, dtype=torch.int64)
+            eot = (pl._eot_rows.to(torch.int64) - torch.arange(C, device=dev, dtype=torch.int64) * Lk)  # eot(c)
+            self._cc = dict(h1=z(B, H), bias=z(B, d), t16=z(B * C, e, dt=torch.float16), t32=z(B * C, e), t_inv=z(B * C),
+                            dt32=z(B * C, e), dtfeat16=z(B * C, e, dt=torch.float16), d_bias=z(B, d), d_h1=z(B, H),
+                            part=z(B, n, d), eot_rows=(bc * Lk + eot.repeat(B)).to(torch.int32).contiguous())
+            self._cc_key = key
+        return self._cc
+
+    def _forward_cocoop(self, image, ready, vpt, deep, task, train: bool) -> torch.Tensor:
+        """Image tower -> normalised features -> meta_net -> B*C instance-conditioned prompts -> text tower on B*C
+        sequences -> logits[b,c] = exp(logit_scale) <img_b, txt_{b,c}>."""
+        pl = self.prompt_learner
+        dev = image.device
+        B, C = image.shape[0], pl.n_cls
+        Lk, d = pl._emb.shape[1], pl._emb.shape[2]
+        head = self.head(dev)
+        hb = head.buffers(B, C)
+        cc = self._cocoop_buffers(dev, B, C)
+        if ready is not None:
+            torch.cuda.current_stream(dev).wait_event(ready)
+        image = image.contiguous()
+        if image.dtype not in (torch.float16, torch.float32):
+            image = image.float()
+        img_feat = self.image_encoder.tower(dev).forward(image, vpt, deep, train=self._img_train)
+        ops.l2norm_fwd(img_feat, hb["i16"], hb["i32"], hb["i_inv"], B, self._embed_dim)
+        W1, b1, W2, b2 = [t.detach().contiguous() for t in pl.meta_params()]
+        ops.metanet_fwd(hb["i32"], W1, b1, W2, b2, cc["h1"], cc["bias"])
+        ctx = pl.cocoop_ctx.detach().contiguous()
+        tt = self.text_encoder.tower(dev)
+        txt = tt.forward_assembled(
+            B * C, Lk, cc["eot_rows"], self._txt_train,
+            lambda x0: ops.cocoop_assemble(pl._emb, ctx, cc["bias"], pl._slot, tt.pos, x0, B, C, Lk, d))
+        ops.l2norm_fwd(txt, cc["t16"], cc["t32"], cc["t_inv"], B * C, self._embed_dim)
+        ops.pair_logits_fwd(hb["i32"], cc["t32"], head.s, hb["logits"], hb["ldc"], B, C, self._embed_dim)
+        logits = hb["logits"]
+        t_dev, ranges = self._task_dev(task, dev)
+        if t_dev is not None:
+            ops.task_mask(logits, hb["ldc"], t_dev, ranges, B, C)
+        return logits
+
+    def _backward_cocoop(self, B: int) -> Dict[str, torch.Tensor]:
+        """dz16 (scaled, from the cross-entropy kernel) -> gradients of cocoop_ctx, meta_net.* (and the visual prompts)."""
+        pl = self.prompt_learner
+        sh = self._shapes
+        C, v, n_deep = sh["C"], sh["v"], sh["n_deep"]
+        dev = pl._emb.device
+        head = self.head(dev)
+        hb = head.buffers(B, C)
+        cc = self._cc
+        e, Lk, d, n = self._embed_dim, pl._emb.shape[1], pl._emb.shape[2], pl.text_n_ctx
+        inv = 1.0 / self.grad_scale
+        views = self.grad_views()
+        ops.pair_logits_bwd(hb["dz16"], hb["ldc"], hb["i32"], cc["t32"], head.s, cc["dt32"], hb["di32"], B, C, e)
+        ops.l2norm_bwd(cc["dt32"], cc["t32"], cc["t_inv"], cc["dtfeat16"], B * C, e)
+        tt = self.text_encoder.tower(dev)
+        dx0 = tt.backward_to_input(cc["dtfeat16"], B * C, Lk, cc["eot_rows"])
+        if dx0.dtype != torch.float16:
+            raise ops._lib.MvlptError("the CoCoOp branch needs the fp16 gradient stream (unset MVLPT_GRAD_STREAM_F32)")
+        ops.cocoop_ctx_grad(dx0, pl._ctx_pos, cc["part"], views["cocoop_ctx"], cc["d_bias"], B, C, Lk, n, d, inv)
+        W1, b1, W2, b2 = [t.detach().contiguous() for t in pl.meta_params()]
+        # meta_net gradients in true scale; its gradient w.r.t. the normalised image features joins the (scaled) one of
+        # the logits before both go back through the L2 normalisation
+        ops.metanet_bwd(cc["d_bias"], hb["i32"], cc["h1"], W1, W2, cc["d_h1"], views["meta_net.linear1.weight"],
+                        views["meta_net.linear1.bias"], views["meta_net.linear2.weight"], views["meta_net.linear2.bias"],
+                        hb["di32"], self.grad_scale)
+        if self._img_train:
+            ops.l2norm_bwd(hb["di32"], hb["i32"], hb["i_inv"], hb["difeat16"], B, e)
+            it = self.image_encoder.tower(dev)
+            d_vpt = views["vpt_embeddings"].view(v, it.d)
+            d_deep = views["vpt_embeddings_deep"] if n_deep is not None else None
+            it.backward(hb["difeat16"], B, v, n_deep, d_vpt, d_deep, inv)
+            if d_deep is None and "vpt_embeddings_deep" in views:
+                ops.zero(views["vpt_embeddings_deep"])
+        return dict(views)
 
     def hold_text_features(self, on: bool):
         """While held, the text tower runs at most once more: its features are constant as long as no prompt parameter
@@ -556,6 +690,8 @@ class CustomCLIP(nn.Module):
             t_dev, ranges = self._task_dev(task, dev)
             dl = dlogits.float().contiguous()
             ops.dlogits_prepare(dl, dl.stride(0), t_dev, ranges, bf["dz16"], bf["ldc"], B, C, self.grad_scale)
+        if pl.cocoop_ctx is not None:
+            return self._backward_cocoop(B)
         head.backward(B, C, need_img=self._img_train, need_txt=self._txt_train)
         inv = 1.0 / self.grad_scale
         views = self.grad_views()

@@ -48,7 +48,7 @@ def make_cfg(case, prec="fp16"):
                             DEEP=case.get("vpt_deep", False)),
                      COOP=NS(N_CTX=case.get("coop_n_ctx", 0), CTX_INIT="", CSC=case.get("csc", False),
                              CLASS_TOKEN_POSITION=case.get("position", "end")),
-                     COCOOP=NS(N_CTX=case.get("cocoop_n_ctx", 0), CTX_INIT="", PREC="fp16")),
+                     COCOOP=NS(N_CTX=case.get("cocoop_n_ctx", 0), CTX_INIT="", PREC="fp32" if prec == "fp32" else "fp16")),
             CUT_CONTEXTLEN=case.get("cut", False), ACT_CKPT=1),
         INPUT=NS(SIZE=(res, res)),
         DATASET=NS(MULTITASK_LABEL_PERTASK=case.get("task_mask", False)),
