@@ -41,7 +41,9 @@ MODES = {
     "coop": (16, 0, False, "identity", "end"),
     "vpt": (0, 8, True, "identity", "end"),
     "upt": (16, 8, True, "transformer", "end"),
+    "cocoop": (0, 0, False, "identity", "end"),  # COCOOP.N_CTX = 4 (instance-conditioned context)
 }
+COCOOP_N_CTX = {"cocoop": 4}
 
 
 def parse_args():
@@ -62,9 +64,11 @@ def parse_args():
 
 def workload_name(a) -> str:
     n, v, deep, method, pos = MODES[a.mode]
-    tag = {"coop": f"MVLPT-CoOp n_ctx={n}", "vpt": f"MVLPT-VPT-deep vctx={v}", "upt": f"MVLPT-UPT n_ctx={n}+vctx={v}"}
-    return (f"{tag[a.mode]} {ARCH} 224x224 batch={a.batch}/GPU C={a.classes} L_t={a.ctx_len} fp16 "
-            f"(BASELINE.json configs[{ {'coop': 1, 'vpt': 2, 'upt': 3}[a.mode] }] shape)")
+    tag = {"coop": f"MVLPT-CoOp n_ctx={n}", "vpt": f"MVLPT-VPT-deep vctx={v}", "upt": f"MVLPT-UPT n_ctx={n}+vctx={v}",
+           "cocoop": f"MVLPT-CoCoOp n_ctx={COCOOP_N_CTX.get(a.mode, 0)}"}
+    ref = {"coop": "BASELINE.json configs[1] shape", "vpt": "BASELINE.json configs[2] shape",
+           "upt": "BASELINE.json configs[3] shape", "cocoop": "SURVEY.md 8f-3, not a BASELINE config"}[a.mode]
+    return f"{tag[a.mode]} {ARCH} 224x224 batch={a.batch}/GPU C={a.classes} L_t={a.ctx_len} fp16 ({ref})"
 
 
 def make_cfg(a):
@@ -76,6 +80,7 @@ def make_cfg(a):
     T.PROJECT_METHOD = method
     T.COOP.N_CTX, T.COOP.CLASS_TOKEN_POSITION = n, pos
     T.VPT.N_CTX, T.VPT.DEEP = v, deep
+    T.COCOOP.N_CTX = COCOOP_N_CTX.get(a.mode, 0)
     cfg.DATASET.COOP = True
     cfg.MODEL.BACKBONE.NAME = ARCH
     return cfg
@@ -85,7 +90,7 @@ def make_problem(a):
     """Synthetic CLIP weights, class-name token ids, data-manager stub."""
     n, v, deep, method, pos = MODES[a.mode]
     sd = synth.synth_clip_state_dict(ARCH, seed=0)
-    toks, name_lens = synth.synth_token_ids(a.classes, n, context_length=a.ctx_len, seed=3)
+    toks, name_lens = synth.synth_token_ids(a.classes, n or COCOOP_N_CTX.get(a.mode, 0), context_length=a.ctx_len, seed=3)
     names = [f"class{c}" for c in range(a.classes)]
     dm = NS(dataset=NS(classnames=names), lab2cname={i: nm for i, nm in enumerate(names)}, num_classes=a.classes,
             num_source_domains=1)
@@ -151,14 +156,16 @@ def cpu_step_fn(a, sd, toks, name_lens, B):
     """One reference train step on the CPU oracle for a B-image sample of the workload (fp32, all host threads)."""
     from oracle import mvlpt_oracle as O
     n, v, deep, method, pos = MODES[a.mode]
-    pp = synth.synth_prompt_params(ARCH, n, v, deep, project_dim=128 if method == "transformer" else 0, seed=0)
+    cc = COCOOP_N_CTX.get(a.mode, 0)
+    pp = synth.synth_prompt_params(ARCH, n, v, deep, project_dim=128 if method == "transformer" else 0, seed=0,
+                                   cocoop_n_ctx=cc)
     res = synth.ARCHS[ARCH]["image_resolution"]
     image = synth.synth_images(B, res, seed=1)
     g = torch.Generator().manual_seed(2)
     label = torch.randint(0, a.classes, (B,), generator=g)
     emb = sd["token_embedding.weight"][toks]
     kw = dict(embedding=emb, eot_index=toks.argmax(-1), name_lens=name_lens, n_ctx=n, v=v, position=pos,
-              upt=method == "transformer")
+              upt=method == "transformer", cocoop_n_ctx=cc)
     params = [p.clone() for p in pp.values()]
     keys = list(pp)
     bufs = [None] * len(params)
@@ -240,7 +247,8 @@ def ours_arm(a):
     cfg = make_cfg(a)
     trainer = MVLPT(cfg, dm=dm, clip_state_dict=sd, device=dev, tokenized_prompts=toks, name_lens=name_lens, dp=dp)
     trainer.num_batches = 1 << 30  # never hits the per-epoch LR update inside the timed loop
-    pp = synth.synth_prompt_params(ARCH, *MODES[a.mode][:3], project_dim=128 if MODES[a.mode][3] == "transformer" else 0)
+    pp = synth.synth_prompt_params(ARCH, *MODES[a.mode][:3], project_dim=128 if MODES[a.mode][3] == "transformer" else 0,
+                                   cocoop_n_ctx=COCOOP_N_CTX.get(a.mode, 0))
     trainer.model.prompt_learner.load_state_dict(pp, strict=False)
 
     n, v, deep, method, pos = MODES[a.mode]
@@ -291,11 +299,13 @@ def ours_arm(a):
                "h2d_bytes_per_step": int(host_batches[0]["img"].numel() * 2 + host_batches[0]["label"].numel() * 8),
                "d2h_bytes_per_step": 8}
 
-    flops = flops_step(synth.ARCHS[ARCH], B, a.classes, a.ctx_len, v, n)
+    cc = COCOOP_N_CTX.get(a.mode, 0)
+    passes = B if cc else 1
+    flops = flops_step(synth.ARCHS[ARCH], B, a.classes, a.ctx_len, v, n or cc, text_passes=passes)
     # rows of the causal text tower behind the last EOT are not computed (they cannot reach any output): the FLOPs
     # actually executed are reported next to the reference's algorithmic count and are the ones "achieved" uses
     Lk = int(trainer.model.prompt_learner.kernel_len)
-    flops_exec = flops_step(synth.ARCHS[ARCH], B, a.classes, Lk, v, n)
+    flops_exec = flops_step(synth.ARCHS[ARCH], B, a.classes, Lk, v, n or cc, text_passes=passes)
     peaks = {}
     pk = REPO / "MEASURED_PEAKS.json"
     if pk.exists():

@@ -12,16 +12,17 @@ def tower_bwd_flops(L: int, d: int, layers: int) -> float:
     return float(layers * (24 * L * d * d + 8 * L * L * d))
 
 
-def flops_step(arch: dict, B: int, C: int, L_t: int, v: int, n_ctx: int) -> float:
-    """One train step: image fwd (+bwd when visual prompts train), text fwd (+bwd when context trains), head."""
+def flops_step(arch: dict, B: int, C: int, L_t: int, v: int, n_ctx: int, text_passes: int = 1) -> float:
+    """One train step: image fwd (+bwd when visual prompts train), text fwd (+bwd when context trains), head.
+    `text_passes` = B for the CoCoOp branch (every image has its own class prompts), else 1."""
     d, ly, p = arch["vision_width"], arch["vision_layers"], arch["vision_patch_size"]
     e, dt, lt = arch["embed_dim"], arch["transformer_width"], arch["transformer_layers"]
     n_p = (arch["image_resolution"] // p) ** 2
     L = 1 + v + n_p
     f = B * (tower_fwd_flops(L, d, ly) + 2 * n_p * d * 3 * p * p + 2 * d * e)
-    f += C * (tower_fwd_flops(L_t, dt, lt) + 2 * dt * e) + 2 * B * C * e
+    f += text_passes * C * (tower_fwd_flops(L_t, dt, lt) + 2 * dt * e) + 2 * B * C * e
     if v > 0:
         f += B * tower_bwd_flops(L, d, ly) + 2 * B * C * e
     if n_ctx > 0:
-        f += C * tower_bwd_flops(L_t, dt, lt) + 2 * B * C * e
+        f += text_passes * C * tower_bwd_flops(L_t, dt, lt) + 2 * B * C * e
     return float(f)
