@@ -105,15 +105,22 @@ int mvlpt_ln_bwd(const void* dy, const void* x, const void* row_index, const voi
  * mvlpt_prompt_grad: grad[j] = inv_scale * sum_b dx[b,1+j] (autograd of the expand over B); with zero_rows the
  *   rows are then cleared in dx (and dx16) because the replaced rows have no upstream.
  *   dx NULL = fp16 gradient stream: the rows are read from dx16.
+ * vpt_dropout (nn.Dropout(VPT.DROPOUT), trainers/mvlpt.py:165; applied after the batch expansion at :76 and :425):
+ *   with drop_p > 0, set_prompt_rows writes prompt[j,c] * keep(b,j,c) / (1-p) and prompt_grad sums
+ *   dx[b,1+j,c] * keep(b,j,c) / (1-p), keep being a counter-based Bernoulli(1-p) draw (16-bit resolution in p) that
+ *   depends only on (seed, slab, b, j, c, B, v, d) — the caller changes `seed` every step and passes the layer as
+ *   `slab`; mvlpt_dropout_keep writes the same mask as uint8 [B, v, d] (tests; replaying a step).  drop_p = 0: no-op.
+ *   Shallow prompts under dropout: embed_assemble, then set_prompt_rows on x0 with slab 0.
  * ------------------------------------------------------------------------------------------------ */
 int mvlpt_im2col(const void* img, int img_f32, void* patches, int B, int H, int W, int p, int Kp, mvlpt_stream_t stream);
 int mvlpt_embed_assemble(const void* pe, const void* cls, const void* pos, const void* gamma, const void* beta,
                          const void* prompt, int prompt_f16, void* x0, int B, int G, int v, int d, float eps,
                          mvlpt_stream_t stream);
-int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d,
-                          mvlpt_stream_t stream);
+int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
+                          uint64_t seed, int slab, mvlpt_stream_t stream);
 int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int d, float inv_scale, int zero_rows,
-                      mvlpt_stream_t stream);
+                      float drop_p, uint64_t seed, int slab, mvlpt_stream_t stream);
+int mvlpt_dropout_keep(void* keep, int B, int v, int d, float drop_p, uint64_t seed, int slab, mvlpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Text prompt assembly (forward_coop, trainers/mvlpt.py:439-515, fused with `+ positional_embedding`,
@@ -194,6 +201,18 @@ int mvlpt_upt_fwd(const mvlpt_upt_desc* d, const void* const* params, void* work
                   void* vpt_out, mvlpt_stream_t stream);
 int mvlpt_upt_bwd(const mvlpt_upt_desc* d, const void* const* params, void* workspace, size_t ws_bytes,
                   const void* d_ctx_out, const void* d_vpt_out, void* const* grads, mvlpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * vpt_proj: the Linear(VPT.PROJECT -> vision width) between the stored visual prompts and the rows the image tower sees
+ * (trainers/mvlpt.py:170-175 construction; applied at :76-77 to every deep-prompt slab and at :425 to the shallow one).
+ *   fwd: out[rows, d] fp32 = emb[rows, p] . W[d, p]^T + b[d]                 (emb, W, b fp16 when param_f16 else fp32)
+ *   bwd: from d_out[rows, d] fp32 (what mvlpt_prompt_grad produced): d_emb[rows, p] = d_out . W  (overwritten),
+ *        dW[d, p] (+)= d_out^T . emb, db[d] (+)= colsum(d_out); `accumulate` != 0 adds into dW / db (second slab).
+ * ------------------------------------------------------------------------------------------------ */
+int mvlpt_vpt_proj_fwd(const void* emb, const void* W, const void* b, int param_f16, void* out, int rows, int d, int p,
+                       mvlpt_stream_t stream);
+int mvlpt_vpt_proj_bwd(const void* d_out, const void* emb, const void* W, int param_f16, void* d_emb, void* dW, void* db,
+                       int rows, int d, int p, int accumulate, mvlpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * CoCoOp branch (trainers/mvlpt.py:260-290 meta_net, :348-374 forward_cocoop, :556-571 per-image text features).

@@ -324,9 +324,30 @@ __global__ void embed_assemble_kernel(const __half* __restrict__ pe, const float
     row_store(row, x0 + (size_t)r * d, d, lane);
 }
 
-// x[b, 1+j] = prompt[j]  (deep prompt replacement before block l >= 1)
+// vpt_dropout (trainers/mvlpt.py:165, applied :76 and :425 AFTER the expansion over the batch, so every (b, j, c) element
+// has its own Bernoulli draw).  Counter-based: the keep bits of the 4 columns c..c+3 of row (slab, b, j) are the four
+// 16-bit lanes of one 64-bit mix of (seed, element-group index); keep <=> lane >= thr, thr = round(p * 65536).  The same
+// function is evaluated by the forward (set_prompt_rows), the backward (prompt_grad) and mvlpt_dropout_keep (tests).
+__device__ __forceinline__ unsigned long long drop_bits(unsigned long long seed, int slab, int b, int j, int c4, int B,
+                                                        int v, int d4) {
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (((((unsigned long long)slab * B + b) * v + j) * d4 + c4) + 1ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+__device__ __forceinline__ float4 drop_scale4(unsigned long long bits, unsigned thr, float keep_scale) {
+    float4 m;
+    m.x = ((unsigned)(bits) & 0xFFFFu) >= thr ? keep_scale : 0.f;
+    m.y = ((unsigned)(bits >> 16) & 0xFFFFu) >= thr ? keep_scale : 0.f;
+    m.z = ((unsigned)(bits >> 32) & 0xFFFFu) >= thr ? keep_scale : 0.f;
+    m.w = ((unsigned)(bits >> 48) & 0xFFFFu) >= thr ? keep_scale : 0.f;
+    return m;
+}
+
+// x[b, 1+j] = prompt[j]  (deep prompt replacement before block l >= 1), times the dropout keep mask / (1-p) when thr > 0
 __global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __restrict__ prompt, int prompt_f16, int B,
-                                       int L, int v, int d) {
+                                       int L, int v, int d, unsigned thr, float keep_scale, unsigned long long seed,
+                                       int slab) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= B * v) return;
@@ -334,7 +355,33 @@ __global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __rest
     Row row;
     if (prompt_f16) row_load_h(row, static_cast<const __half*>(prompt) + (size_t)j * d, d, lane);
     else row_load(row, static_cast<const float*>(prompt) + (size_t)j * d, d, lane);
+    if (thr) {
+#pragma unroll
+        for (int i = 0; i < kMaxV4; ++i) {
+            const int c4 = lane + 32 * i;
+            if (c4 * 4 < d) {
+                const float4 m = drop_scale4(drop_bits(seed, slab, b, j, c4, B, v, d >> 2), thr, keep_scale);
+                row.v[i].x *= m.x; row.v[i].y *= m.y; row.v[i].z *= m.z; row.v[i].w *= m.w;
+            }
+        }
+    }
     row_store(row, x + ((size_t)b * L + 1 + j) * d, d, lane);
+}
+
+// keep[b, j, c] in {0,1}: the mask the two kernels above/below apply (for tests and for replaying a step elsewhere)
+__global__ void dropout_keep_kernel(unsigned char* __restrict__ keep, int B, int v, int d, unsigned thr,
+                                    unsigned long long seed, int slab) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int d4 = d >> 2;
+    if (i >= B * v * d4) return;
+    const int c4 = i % d4, j = (i / d4) % v, b = i / (d4 * v);
+    const unsigned long long bits = drop_bits(seed, slab, b, j, c4, B, v, d4);
+    uchar4 o;
+    o.x = ((unsigned)(bits) & 0xFFFFu) >= thr;
+    o.y = ((unsigned)(bits >> 16) & 0xFFFFu) >= thr;
+    o.z = ((unsigned)(bits >> 32) & 0xFFFFu) >= thr;
+    o.w = ((unsigned)(bits >> 48) & 0xFFFFu) >= thr;
+    reinterpret_cast<uchar4*>(keep)[i] = o;
 }
 
 // grad[j, :] = inv_scale * sum_b dx[b, 1+j, :]; optionally zero those rows (they do not flow further back)
@@ -342,7 +389,7 @@ __global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __rest
 // and the 16 partial sums are added in a fixed order through shared memory (deterministic, no atomics).
 __global__ void __launch_bounds__(256)
 prompt_grad_kernel(float* __restrict__ dx, __half* __restrict__ dx16, float* __restrict__ grad, int B, int L, int v, int d,
-                   float inv_scale, int zero_rows) {
+                   float inv_scale, int zero_rows, unsigned thr, float keep_scale, unsigned long long seed, int slab) {
     __shared__ float4 part[16][17];
     const int j = blockIdx.y;
     const int cg = threadIdx.x & 15, bl = threadIdx.x >> 4;
@@ -365,6 +412,10 @@ prompt_grad_kernel(float* __restrict__ dx, __half* __restrict__ dx16, float* __r
                         const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
                         const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
                         t[k] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
+                    if (thr) {  // autograd of the dropout: the same keep mask / (1-p) the forward applied
+                        const float4 m = drop_scale4(drop_bits(seed, slab, b, j, c >> 2, B, v, d >> 2), thr, keep_scale);
+                        t[k].x *= m.x; t[k].y *= m.y; t[k].z *= m.z; t[k].w *= m.w;
                     }
                 }
             }
@@ -537,29 +588,61 @@ int mvlpt_embed_assemble(const void* pe, const void* cls, const void* pos, const
     return launched("embed_assemble");
 }
 
-int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d,
-                          mvlpt_stream_t stream) {
+namespace {
+// p in [0,1) -> (threshold on a 16-bit lane, 1/(1-p)); p = 0 -> (0, 1): no dropout
+int drop_params(float p, const char* who, unsigned& thr, float& keep_scale) {
+    if (!(p >= 0.f) || p >= 1.f) return fail(MVLPT_EINVAL, "%s: dropout probability must be in [0, 1)", who);
+    thr = static_cast<unsigned>(p * 65536.f + 0.5f);
+    keep_scale = 1.f / (1.f - p);
+    return MVLPT_OK;
+}
+}  // namespace
+
+int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
+                          uint64_t seed, int slab, mvlpt_stream_t stream) {
     if (!x || !prompt) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows: null argument");
     if (B <= 0 || v <= 0 || L < 1 + v) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows: bad sizes");
     int rc = check_d(d, "mvlpt_set_prompt_rows");
     if (rc) return rc;
+    unsigned thr;
+    float ks;
+    if ((rc = drop_params(drop_p, "mvlpt_set_prompt_rows", thr, ks))) return rc;
     if ((rc = require_sm100())) return rc;
     set_prompt_rows_kernel<<<cdiv(B * v, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<float*>(x), prompt, prompt_f16, B, L, v, d);
+        static_cast<float*>(x), prompt, prompt_f16, B, L, v, d, thr, ks, seed, slab);
     return launched("set_prompt_rows");
 }
 
 int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int d, float inv_scale, int zero_rows,
-                      mvlpt_stream_t stream) {
+                      float drop_p, uint64_t seed, int slab, mvlpt_stream_t stream) {
     if ((!dx && !dx16) || !grad) return fail(MVLPT_EINVAL, "mvlpt_prompt_grad: null argument");
     if (B <= 0 || v <= 0 || L < 1 + v) return fail(MVLPT_EINVAL, "mvlpt_prompt_grad: bad sizes");
     int rc = check_d(d, "mvlpt_prompt_grad");
     if (rc) return rc;
+    unsigned thr;
+    float ks;
+    if ((rc = drop_params(drop_p, "mvlpt_prompt_grad", thr, ks))) return rc;
     if ((rc = require_sm100())) return rc;
     dim3 grid(cdiv(d, 64), v);
     prompt_grad_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<float*>(dx), static_cast<__half*>(dx16), static_cast<float*>(grad), B, L, v, d, inv_scale, zero_rows);
+        static_cast<float*>(dx), static_cast<__half*>(dx16), static_cast<float*>(grad), B, L, v, d, inv_scale, zero_rows,
+        thr, ks, seed, slab);
     return launched("prompt_grad");
+}
+
+int mvlpt_dropout_keep(void* keep, int B, int v, int d, float drop_p, uint64_t seed, int slab, mvlpt_stream_t stream) {
+    if (!keep) return fail(MVLPT_EINVAL, "mvlpt_dropout_keep: null argument");
+    if (B <= 0 || v <= 0) return fail(MVLPT_EINVAL, "mvlpt_dropout_keep: bad sizes");
+    int rc = check_d(d, "mvlpt_dropout_keep");
+    if (rc) return rc;
+    unsigned thr;
+    float ks;
+    if ((rc = drop_params(drop_p, "mvlpt_dropout_keep", thr, ks))) return rc;
+    if ((rc = require_sm100())) return rc;
+    const int n = B * v * (d >> 2);
+    dropout_keep_kernel<<<cdiv(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        static_cast<unsigned char*>(keep), B, v, d, thr, seed, slab);
+    return launched("dropout_keep");
 }
 
 int mvlpt_text_assemble(const void* emb, const void* ctx, int ctx_f16, const void* slot, const void* pos, void* x0,

@@ -336,4 +336,28 @@ int mvlpt_upt_bwd(const mvlpt_upt_desc* d, const void* const* P, void* workspace
     return c.rc;
 }
 
+int mvlpt_vpt_proj_fwd(const void* emb, const void* W, const void* b, int param_f16, void* out, int rows, int d, int p,
+                       mvlpt_stream_t stream) {
+    if (!emb || !W || !b || !out) return fail(MVLPT_EINVAL, "mvlpt_vpt_proj_fwd: null argument");
+    if (rows <= 0 || d <= 0 || p <= 0) return fail(MVLPT_EINVAL, "mvlpt_vpt_proj_fwd: sizes must be positive");
+    int rc = require_sm100();
+    if (rc) return rc;
+    Ctx c{static_cast<cudaStream_t>(stream), 0};
+    linear(c, emb, param_f16, W, b, param_f16, nullptr, static_cast<float*>(out), rows, d, p);
+    return c.rc;
+}
+
+int mvlpt_vpt_proj_bwd(const void* d_out, const void* emb, const void* W, int param_f16, void* d_emb, void* dW, void* db,
+                       int rows, int d, int p, int accumulate, mvlpt_stream_t stream) {
+    if (!d_out || !emb || !W || !d_emb || !dW || !db) return fail(MVLPT_EINVAL, "mvlpt_vpt_proj_bwd: null argument");
+    if (rows <= 0 || d <= 0 || p <= 0) return fail(MVLPT_EINVAL, "mvlpt_vpt_proj_bwd: sizes must be positive");
+    int rc = require_sm100();
+    if (rc) return rc;
+    Ctx c{static_cast<cudaStream_t>(stream), 0};
+    const float* dY = static_cast<const float*>(d_out);
+    wgrad(c, dY, emb, param_f16, static_cast<float*>(dW), static_cast<float*>(db), rows, d, p, accumulate);
+    dgrad(c, dY, W, param_f16, static_cast<float*>(d_emb), rows, d, p);
+    return c.rc;
+}
+
 }  // extern "C"

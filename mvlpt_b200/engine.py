@@ -180,8 +180,10 @@ class ImageTower:
         return [l for l in range(self.layers) if l == 0 or l <= n_deep]
 
     def forward(self, image: torch.Tensor, vpt: Optional[torch.Tensor], vpt_deep: Optional[torch.Tensor],
-                train: bool) -> torch.Tensor:
-        """image [B,3,H,W] fp16/fp32; vpt [1,v,d] or None; vpt_deep [n_deep,v,d] or None -> features fp32 [B,e]."""
+                train: bool, drop_p: float = 0.0, drop_seed: int = 0) -> torch.Tensor:
+        """image [B,3,H,W] fp16/fp32; vpt [1,v,d] or None; vpt_deep [n_deep,v,d] or None -> features fp32 [B,e].
+        drop_p > 0: vpt_dropout in training mode (trainers/mvlpt.py:76,425) with the counter-based mask of `drop_seed`;
+        the backward of the same buffers replays it."""
         B = image.shape[0]
         v = 0 if vpt is None else vpt.shape[1]
         bf = self.buffers(B, v, train)
@@ -190,6 +192,11 @@ class ImageTower:
         ops.gemm(bf["patches"], self.conv_w, bf["pe"])
         ops.embed_assemble(bf["pe"], self.cls, self.pos, self.ln_pre_g, self.ln_pre_b, vpt, a.x_in(0), B, self.G, v,
                            self.d)
+        if v == 0:
+            drop_p = 0.0
+        if drop_p > 0.0:
+            ops.set_prompt_rows(a.x_in(0), vpt, B, a.L, v, self.d, drop_p, drop_seed, 0)
+        bf["drop"] = (drop_p, drop_seed)
         run = self.executed_layers(None if vpt_deep is None else vpt_deep.shape[0])
         last = a.x_in(0)
         for l in run:
@@ -198,7 +205,7 @@ class ImageTower:
                 src = a.x_in(l)
                 if a.train and last is not src:
                     src.copy_(last)  # only reachable through the skipped-layer quirk
-                ops.set_prompt_rows(src, vpt_deep[l - 1], B, a.L, v, self.d)
+                ops.set_prompt_rows(src, vpt_deep[l - 1], B, a.L, v, self.d, drop_p, drop_seed, l)
             block_forward(self.blocks[l], a, l, causal=False)
             last = a.x_out(l)
         bf["final"] = last
@@ -212,6 +219,7 @@ class ImageTower:
         """dfeat16 fp16 [B,e] (scaled) -> grad_vpt fp32 [v,d], grad_deep fp32 [n_deep,v,d] (unscaled)."""
         bf = self.buffers(B, v, True)
         a: TowerBuffers = bf["act"]
+        drop_p, drop_seed = bf.get("drop", (0.0, 0))
         ops.gemm(dfeat16, self.proj, bf["dpool"])
         if a.dx is not None:
             ops.zero(a.dx)
@@ -221,8 +229,9 @@ class ImageTower:
         for l in reversed(bf["run"]):
             block_backward(self.blocks[l], a, l, causal=False)
             if n_deep is not None and l >= 1:
-                ops.prompt_grad(a.dx, a.dx16, grad_deep[l - 1], B, a.L, v, self.d, inv_scale, zero_rows=True)
-        ops.prompt_grad(a.dx, None if a.dx is not None else a.dx16, grad_vpt, B, a.L, v, self.d, inv_scale, zero_rows=False)
+                ops.prompt_grad(a.dx, a.dx16, grad_deep[l - 1], B, a.L, v, self.d, inv_scale, True, drop_p, drop_seed, l)
+        ops.prompt_grad(a.dx, None if a.dx is not None else a.dx16, grad_vpt, B, a.L, v, self.d, inv_scale, False,
+                        drop_p, drop_seed, 0)
 
 
 class TextTower:

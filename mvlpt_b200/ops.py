@@ -140,14 +140,20 @@ def embed_assemble(pe, cls, pos, gamma, beta, prompt, x0, B, G, v, d):
                                           v, d, LN_EPS, _stream()), "mvlpt_embed_assemble")
 
 
-def set_prompt_rows(x, prompt, B, L, v, d):
-    check(_lib.lib().mvlpt_set_prompt_rows(_p(x), _p(prompt), int(prompt.dtype == torch.float16), B, L, v, d, _stream()),
-          "mvlpt_set_prompt_rows")
+def set_prompt_rows(x, prompt, B, L, v, d, drop_p=0.0, seed=0, slab=0):
+    check(_lib.lib().mvlpt_set_prompt_rows(_p(x), _p(prompt), int(prompt.dtype == torch.float16), B, L, v, d, float(drop_p),
+                                           int(seed), int(slab), _stream()), "mvlpt_set_prompt_rows")
 
 
-def prompt_grad(dx, dx16, grad, B, L, v, d, inv_scale, zero_rows):
+def dropout_keep(keep, B, v, d, drop_p, seed, slab):
+    """uint8 [B,v,d]: the keep mask set_prompt_rows / prompt_grad use for (seed, slab)."""
+    check(_lib.lib().mvlpt_dropout_keep(_p(keep), B, v, d, float(drop_p), int(seed), int(slab), _stream()),
+          "mvlpt_dropout_keep")
+
+
+def prompt_grad(dx, dx16, grad, B, L, v, d, inv_scale, zero_rows, drop_p=0.0, seed=0, slab=0):
     check(_lib.lib().mvlpt_prompt_grad(_p(dx), _p(dx16), _p(grad), B, L, v, d, float(inv_scale), int(zero_rows),
-                                       _stream()), "mvlpt_prompt_grad")
+                                       float(drop_p), int(seed), int(slab), _stream()), "mvlpt_prompt_grad")
 
 
 def text_assemble(emb, ctx, slot, pos, x0, C, Lt, n_ctx, d, csc):
@@ -208,7 +214,20 @@ def _pf16(*ts):
         return 1
     if dt == {torch.float32}:
         return 0
-    raise _lib.MvlptError(f"meta-net parameters must be all fp16 or all fp32, got {dt}")
+    raise _lib.MvlptError(f"parameters of one module must be all fp16 or all fp32, got {dt}")
+
+
+def vpt_proj_fwd(emb, W, b, out):
+    """out[rows,d] fp32 = emb[rows,p] . W[d,p]^T + b   (vpt_proj, trainers/mvlpt.py:170-175)."""
+    rows, p = emb.numel() // emb.shape[-1], emb.shape[-1]
+    check(_lib.lib().mvlpt_vpt_proj_fwd(_p(emb), _p(W), _p(b), _pf16(emb, W, b), _p(out), rows, W.shape[0], p, _stream()),
+          "mvlpt_vpt_proj_fwd")
+
+
+def vpt_proj_bwd(d_out, emb, W, d_emb, dW, db, accumulate):
+    rows, p = emb.numel() // emb.shape[-1], emb.shape[-1]
+    check(_lib.lib().mvlpt_vpt_proj_bwd(_p(d_out), _p(emb), _p(W), _pf16(emb, W), _p(d_emb), _p(dW), _p(db), rows, W.shape[0], p,
+                                        int(accumulate), _stream()), "mvlpt_vpt_proj_bwd")
 
 
 def metanet_fwd(imf, W1, b1, W2, b2, h1, bias):

@@ -98,22 +98,27 @@ def synth_clip_state_dict(arch: str | dict, seed: int = 0) -> "OrderedDict[str, 
 
 
 def synth_prompt_params(arch: str | dict, coop_n_ctx: int, vpt_n_ctx: int, vpt_deep: bool, csc_classes: int = 0,
-                        project_dim: int = 0, seed: int = 0, cocoop_n_ctx: int = 0) -> dict:
+                        project_dim: int = 0, seed: int = 0, cocoop_n_ctx: int = 0, vpt_project: int = -1) -> dict:
     """Trainable prompt tensors under the reference's prompt_learner key names (trainers/mvlpt.py:169-257).
 
     Values are fp16-representable (the reference creates them in CLIP's dtype, trainers/mvlpt.py:151,188-197,222-225).
-    `project_dim` > 0 adds the UPT projection modules (PROJECT_METHOD='transformer').
+    `project_dim` > 0 adds the UPT projection modules (PROJECT_METHOD='transformer'); `vpt_project` > -1 stores the
+    visual prompts at that width and adds the vpt_proj Linear (:170-175).
     """
     a = ARCHS[arch] if isinstance(arch, str) else arch
     vw, vl, p, tw = a["vision_width"], a["vision_layers"], a["vision_patch_size"], a["transformer_width"]
     out = {}
     if vpt_n_ctx:
-        val = math.sqrt(6.0 / float(3 * p * p + vw))
-        u = torch.rand(1, vpt_n_ctx, vw, generator=_gen("vpt_embeddings", seed)) * 2 - 1
+        pw = vpt_project if vpt_project > -1 else vw
+        val = math.sqrt(6.0 / float(3 * p * p + pw))
+        u = torch.rand(1, vpt_n_ctx, pw, generator=_gen("vpt_embeddings", seed)) * 2 - 1
         out["vpt_embeddings"] = (u * val).half().float()
         if vpt_deep:
-            u = torch.rand(vl - 1, vpt_n_ctx, vw, generator=_gen("vpt_embeddings_deep", seed)) * 2 - 1
+            u = torch.rand(vl - 1, vpt_n_ctx, pw, generator=_gen("vpt_embeddings_deep", seed)) * 2 - 1
             out["vpt_embeddings_deep"] = (u * val).half().float()
+        if vpt_project > -1:  # kaiming_normal_(fan_out): std = sqrt(2 / d)
+            out["vpt_proj.weight"] = _normal("vpt_proj.weight", seed, (vw, pw), (2.0 / vw) ** 0.5, fp16=True)
+            out["vpt_proj.bias"] = _normal("vpt_proj.bias", seed, (vw,), 0.02, fp16=True)
     if coop_n_ctx:
         shape = (csc_classes, coop_n_ctx, tw) if csc_classes else (coop_n_ctx, tw)
         out["ctx"] = _normal("ctx", seed, shape, 0.02, fp16=True)

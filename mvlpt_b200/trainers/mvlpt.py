@@ -30,7 +30,7 @@ from .. import engine as E
 from .. import ops
 from ..clip_model import FrozenCLIP, as_state_dict, build_model
 from ..tokenizer import EOT, SOT, get_tokenizer, tokenize
-from ..upt import UptProjection
+from ..upt import UptProjection, VptProjection
 
 __all__ = ["load_clip_to_cpu", "ImageEncoder", "TextEncoder", "MultitaskVLPromptLearner", "CustomCLIP", "MVLPT"]
 
@@ -120,27 +120,30 @@ class MultitaskVLPromptLearner(nn.Module):
         cfg_imsize = cfg.INPUT.SIZE[0]
         assert cfg_imsize == clip_imsize, f"cfg_imsize ({cfg_imsize}) must equal to clip_imsize ({clip_imsize})"
 
-        self.vpt_dropout = nn.Dropout(T.VPT.DROPOUT)
-        if T.VPT.DROPOUT != 0:
-            raise NotImplementedError("VPT.DROPOUT > 0 is not implemented (reference default 0.0, train.py:139)")
+        self.vpt_dropout = nn.Dropout(T.VPT.DROPOUT)  # applied inside the tower kernels (drop_state below)
+        self.drop_seed_override: Optional[int] = None
         self.vpt_deep = T.VPT.DEEP
         self.vpt_embeddings = None
         self.vpt_embeddings_deep = None
         prompt_prefix = None
         if vpt_n_ctx != 0:
-            if T.VPT.PROJECT > -1:
-                raise NotImplementedError("VPT.PROJECT > -1 (vpt_proj Linear, trainers/mvlpt.py:170-175) not implemented")
-            self.vpt_proj = nn.Identity()
+            if T.VPT.PROJECT > -1:  # trainers/mvlpt.py:170-175: prompts stored at width PROJECT, Linear up to the tower's
+                vpt_dim = T.VPT.PROJECT
+                self.vpt_proj = nn.Linear(vpt_dim, vpt_ctx_dim).type(dtype)
+                nn.init.kaiming_normal_(self.vpt_proj.weight, a=0, mode="fan_out")
+            else:
+                vpt_dim = vpt_ctx_dim
+                self.vpt_proj = nn.Identity()
             if T.VPT.CTX_INIT:
                 raise ValueError("CTX initiation scheme is not supported")
-            val = math.sqrt(6.0 / float(3 * reduce(mul, (patch, patch), 1) + vpt_ctx_dim))
-            self.vpt_embeddings = nn.Parameter(torch.zeros(1, vpt_n_ctx, vpt_ctx_dim, dtype=dtype))
+            val = math.sqrt(6.0 / float(3 * reduce(mul, (patch, patch), 1) + vpt_dim))
+            self.vpt_embeddings = nn.Parameter(torch.zeros(1, vpt_n_ctx, vpt_dim, dtype=dtype))
             nn.init.uniform_(self.vpt_embeddings.data, -val, val)
             if self.vpt_deep:
                 self.vision_layers = len([k for k in clip_model.state_dict().keys()
                                           if k.startswith("visual.") and k.endswith(".attn.in_proj_weight")])
                 self.vpt_embeddings_deep = nn.Parameter(
-                    torch.zeros(self.vision_layers - 1, vpt_n_ctx, vpt_ctx_dim, dtype=dtype))
+                    torch.zeros(self.vision_layers - 1, vpt_n_ctx, vpt_dim, dtype=dtype))
                 nn.init.uniform_(self.vpt_embeddings_deep.data, -val, val)
             prompt_prefix = "a photo of a "
 
@@ -167,6 +170,12 @@ class MultitaskVLPromptLearner(nn.Module):
             if method == "identity":
                 pass
             elif method == "transformer":
+                if T.VPT.PROJECT > -1 and T.VPT.PROJECT != vpt_ctx_dim:
+                    # the reference sizes mvlpt_proj_ctx_vpt_pre for the tower width (trainers/mvlpt.py:243-246) and then
+                    # feeds it PROJECT-wide prompts: a shape error there, an explicit one here
+                    raise NotImplementedError("VPT.PROJECT together with PROJECT_METHOD='transformer' is shape-inconsistent "
+                                              "in the reference (trainers/mvlpt.py:243-246,389) unless PROJECT equals the "
+                                              "vision width; not supported")
                 pd = T.PROJECT_DIM
                 ident = lambda: nn.Identity()
                 self.mvlpt_proj_ctx_vpt_pre, self.mvlpt_proj_ctx_vpt_post = ident(), ident()
@@ -265,6 +274,28 @@ class MultitaskVLPromptLearner(nn.Module):
         self.register_buffer("_ctx_pos", ctx_pos, persistent=False)
         self.register_buffer("_eot_rows", (torch.arange(n_cls) * Lk + eot).to(torch.int32), persistent=False)
         self._upt: Optional[UptProjection] = None
+        self._vproj: Optional[VptProjection] = None
+
+    # ---- vpt_dropout -----------------------------------------------------------------------------------------
+    def drop_state(self):
+        """(p, seed) of this forward pass: nn.Dropout semantics — active iff the module is in training mode and p > 0.
+        The seed of the counter-based mask comes from torch's CPU generator (so torch.manual_seed reproduces a run)."""
+        p = float(self.vpt_dropout.p)
+        if p <= 0.0 or not self.vpt_dropout.training or self.vpt_embeddings is None:
+            return 0.0, 0
+        if self.drop_seed_override is not None:
+            return p, int(self.drop_seed_override)
+        return p, int(torch.randint(0, 2 ** 62, (1,)).item())
+
+    # ---- vpt_proj --------------------------------------------------------------------------------------------
+    @property
+    def uses_vpt_proj(self) -> bool:
+        return self.vpt_embeddings is not None and isinstance(self.vpt_proj, nn.Linear)
+
+    def vproj(self) -> "VptProjection":
+        if self._vproj is None:
+            self._vproj = VptProjection(self)
+        return self._vproj
 
     # ---- UPT -------------------------------------------------------------------------------------------------
     @property
@@ -291,6 +322,9 @@ class MultitaskVLPromptLearner(nn.Module):
                 return x
             vpt_embeddings = self.vpt_embeddings
         B = x.shape[0]
+        if self.uses_vpt_proj:
+            vpt_embeddings = self.vproj().forward(vpt_embeddings, None)[0]
+        vpt_embeddings = self.vpt_dropout(vpt_embeddings.expand(B, -1, -1))
         return torch.cat([x[:, :1, :], vpt_embeddings.expand(B, -1, -1).to(x.dtype), x[:, 1:, :]], dim=1)
 
     def forward_coop(self, ctx=None):
@@ -378,7 +412,11 @@ class ImageEncoder(nn.Module):
         if x.dtype not in (torch.float16, torch.float32):
             x = x.float()
         cont = lambda t: None if t is None else t.detach().contiguous()
-        feat = self.tower(x.device).forward(x, cont(vpt_embeddings), cont(deep), train=False)
+        vpt_embeddings, deep = cont(vpt_embeddings), cont(deep)
+        if vpt_embeddings is not None and m.uses_vpt_proj:
+            vpt_embeddings, deep = m.vproj().forward(vpt_embeddings, deep)
+        drop_p, drop_seed = m.drop_state()
+        feat = self.tower(x.device).forward(x, vpt_embeddings, deep, False, drop_p, drop_seed)
         return feat.to(self._out_dtype)
 
 
@@ -519,6 +557,8 @@ class CustomCLIP(nn.Module):
             deep = None
         cont = lambda t: None if t is None else t.detach().contiguous()
         ctx, vpt, deep = cont(ctx), cont(vpt), cont(deep)
+        if vpt is not None and pl.uses_vpt_proj:
+            vpt, deep = pl.vproj().forward(vpt, deep)
         self._img_train = bool(train and vpt is not None)
         self._txt_train = bool(train and (ctx is not None or pl.cocoop_ctx is not None))
         self._shapes = dict(B=B, C=C, v=0 if vpt is None else vpt.shape[1],
@@ -538,7 +578,8 @@ class CustomCLIP(nn.Module):
         image = image.contiguous()
         if image.dtype not in (torch.float16, torch.float32):
             image = image.float()
-        img_feat = self.image_encoder.tower(dev).forward(image, vpt, deep, train=self._img_train)
+        drop_p, drop_seed = pl.drop_state()
+        img_feat = self.image_encoder.tower(dev).forward(image, vpt, deep, self._img_train, drop_p, drop_seed)
         logits = head.logits(img_feat, C)
         t_dev, ranges = self._task_dev(task, dev)
         if t_dev is not None:
@@ -577,7 +618,8 @@ class CustomCLIP(nn.Module):
         image = image.contiguous()
         if image.dtype not in (torch.float16, torch.float32):
             image = image.float()
-        img_feat = self.image_encoder.tower(dev).forward(image, vpt, deep, train=self._img_train)
+        drop_p, drop_seed = pl.drop_state()
+        img_feat = self.image_encoder.tower(dev).forward(image, vpt, deep, self._img_train, drop_p, drop_seed)
         ops.l2norm_fwd(img_feat, hb["i16"], hb["i32"], hb["i_inv"], B, self._embed_dim)
         W1, b1, W2, b2 = [t.detach().contiguous() for t in pl.meta_params()]
         ops.metanet_fwd(hb["i32"], W1, b1, W2, b2, cc["h1"], cc["bias"])
@@ -622,9 +664,14 @@ class CustomCLIP(nn.Module):
         if self._img_train:
             ops.l2norm_bwd(hb["di32"], hb["i32"], hb["i_inv"], hb["difeat16"], B, e)
             it = self.image_encoder.tower(dev)
-            d_vpt = views["vpt_embeddings"].view(v, it.d)
-            d_deep = views["vpt_embeddings_deep"] if n_deep is not None else None
+            if pl.uses_vpt_proj:
+                d_vpt, d_deep = pl.vproj().grad_input_views(n_deep)
+            else:
+                d_vpt = views["vpt_embeddings"].view(v, it.d)
+                d_deep = views["vpt_embeddings_deep"] if n_deep is not None else None
             it.backward(hb["difeat16"], B, v, n_deep, d_vpt, d_deep, inv)
+            if pl.uses_vpt_proj:
+                pl.vproj().backward(views, n_deep)
             if d_deep is None and "vpt_embeddings_deep" in views:
                 ops.zero(views["vpt_embeddings_deep"])
         return dict(views)
@@ -700,12 +747,16 @@ class CustomCLIP(nn.Module):
         d_ctx = d_vpt = d_deep = None
         if self._img_train:
             it = self.image_encoder.tower(dev)
-            if proj:
+            if pl.uses_vpt_proj:
+                d_vpt, d_deep = pl.vproj().grad_input_views(n_deep)
+            elif proj:
                 _, d_vpt, d_deep = pl.upt().grad_input_views()
             else:
                 d_vpt = views["vpt_embeddings"].view(v, it.d)
                 d_deep = views["vpt_embeddings_deep"] if n_deep is not None else None
             it.backward(bf["difeat16"], B, v, n_deep, d_vpt, d_deep, inv)
+            if pl.uses_vpt_proj:
+                pl.vproj().backward(views, n_deep)
         if self._txt_train:
             tt = self.text_encoder.tower(dev)
             if proj:
@@ -730,7 +781,7 @@ class CustomCLIP(nn.Module):
             pl.upt().backward(views)
             grads = dict(views)
         else:
-            for k in ("ctx", "vpt_embeddings", "vpt_embeddings_deep"):
+            for k in ("ctx", "vpt_embeddings", "vpt_embeddings_deep", "vpt_proj.weight", "vpt_proj.bias"):
                 if k in views:
                     grads[k] = views[k]
             if d_deep is None and "vpt_embeddings_deep" in grads:

@@ -99,3 +99,69 @@ class UptProjection:
         _lib.check(_lib.lib().mvlpt_upt_bwd(ctypes.byref(self.desc), P, self.ws.data_ptr(), self.ws.numel() * 4,
                                             self.d_ctx_out.data_ptr(), self.d_vpt_out.data_ptr(), G, self._stream()),
                    "mvlpt_upt_bwd")
+
+
+class VptProjection:
+    """vpt_proj = Linear(VPT.PROJECT -> vision width) (trainers/mvlpt.py:170-175), applied to the shallow prompts (:425)
+    and to every deep slab (:76-77) before they enter the image tower; forward and backward incl. the weight gradient,
+    over mvlpt_vpt_proj_fwd / mvlpt_vpt_proj_bwd (csrc/upt.cu).  Outputs are fp32 (the reference rounds them to CLIP's
+    dtype; the tower rounds once, when it writes the rows)."""
+
+    def __init__(self, prompt_learner):
+        pl = prompt_learner
+        self.pl = pl
+        W = pl.vpt_proj.weight
+        self.d, self.p = W.shape
+        self.v = pl.vpt_n_ctx
+        n_deep = pl.vpt_embeddings_deep.shape[0] if pl.vpt_embeddings_deep is not None else 0
+        rows = (1 + n_deep) * self.v
+        dev = W.device
+        self.out = torch.empty(rows, self.d, device=dev, dtype=torch.float32)
+        self.d_out = torch.zeros(rows, self.d, device=dev, dtype=torch.float32)
+        self._emb = None
+
+    def _params(self):
+        W, b = self.pl.vpt_proj.weight.detach(), self.pl.vpt_proj.bias.detach()
+        if not W.is_cuda:
+            raise _lib.MvlptError("vpt_proj: parameters must live on a CUDA device")
+        return W.contiguous(), b.contiguous()
+
+    def forward(self, vpt: torch.Tensor, deep: Optional[torch.Tensor]):
+        """(vpt [1,v,p], deep [n_deep,v,p] | None) -> fp32 ([1,v,d], [n_deep,v,d] | None), views of one buffer."""
+        from . import ops
+        W, b = self._params()
+        v, d = self.v, self.d
+        vpt = vpt.detach().to(W.dtype).contiguous()
+        if vpt.shape[-1] != self.p or vpt.numel() != v * self.p:
+            raise _lib.MvlptError(f"vpt_proj: expected prompts of shape [1,{v},{self.p}], got {tuple(vpt.shape)}")
+        ops.vpt_proj_fwd(vpt, W, b, self.out[:v])
+        out_deep = None
+        if deep is not None:
+            deep = deep.detach().to(W.dtype).contiguous()
+            nd = deep.shape[0]
+            if (1 + nd) * v > self.out.shape[0]:
+                self.out = torch.empty((1 + nd) * v, d, device=W.device, dtype=torch.float32)
+                self.d_out = torch.zeros((1 + nd) * v, d, device=W.device, dtype=torch.float32)
+                ops.vpt_proj_fwd(vpt, W, b, self.out[:v])
+            ops.vpt_proj_fwd(deep, W, b, self.out[v:(1 + nd) * v])
+            out_deep = self.out[v:(1 + nd) * v].view(nd, v, d)
+        self._emb = (vpt, deep)
+        return self.out[:v].view(1, v, d), out_deep
+
+    def grad_input_views(self, n_deep):
+        """Buffers the image tower writes d(projected prompts) into (fp32, unscaled)."""
+        v = self.v
+        deep = self.d_out[v:(1 + n_deep) * v].view(n_deep, v, self.d) if n_deep else None
+        return self.d_out[:v], deep
+
+    def backward(self, grad_views: Dict[str, torch.Tensor], n_deep):
+        """d_out (filled by the tower) -> gradients of vpt_embeddings[_deep], vpt_proj.weight, vpt_proj.bias."""
+        from . import ops
+        W, _ = self._params()
+        vpt, deep = self._emb
+        v = self.v
+        dW, db = grad_views["vpt_proj.weight"], grad_views["vpt_proj.bias"]
+        ops.vpt_proj_bwd(self.d_out[:v], vpt, W, grad_views["vpt_embeddings"], dW, db, accumulate=False)
+        if n_deep and deep is not None:
+            ops.vpt_proj_bwd(self.d_out[v:(1 + n_deep) * v], deep, W, grad_views["vpt_embeddings_deep"], dW, db,
+                             accumulate=True)

@@ -69,7 +69,8 @@ def make_cfg(case) -> NS:
         TRAINER=NS(
             MVLPT=NS(PREC="fp32", PROJECT_METHOD=case.get("project_method", "identity"),
                      PROJECT_DIM=case.get("project_dim", 128),
-                     VPT=NS(N_CTX=case.get("vpt_n_ctx", 0), CTX_INIT="", DROPOUT=0.0, PROJECT=-1,
+                     VPT=NS(N_CTX=case.get("vpt_n_ctx", 0), CTX_INIT="", DROPOUT=case.get("vpt_dropout", 0.0),
+                            PROJECT=case.get("vpt_project", -1),
                             DEEP=case.get("vpt_deep", False)),
                      COOP=NS(N_CTX=case.get("coop_n_ctx", 0), CTX_INIT="", CSC=case.get("csc", False),
                              CLASS_TOKEN_POSITION=case.get("position", "end")),
@@ -98,6 +99,10 @@ CASES = [
          cut=True, project_method="transformer", project_dim=32, B=3, C=5),
     dict(name="tiny_cocoop", arch="tiny", cocoop_n_ctx=4, B=3, C=5),
     dict(name="tiny_cocoop_vpt_deep", arch="tiny", cocoop_n_ctx=4, vpt_n_ctx=3, vpt_deep=True, B=2, C=6),
+    dict(name="tiny_vpt_deep_project", arch="tiny", vpt_n_ctx=4, vpt_deep=True, vpt_project=24, B=3, C=5),
+    dict(name="tiny_vpt_shallow_project_coop", arch="tiny", vpt_n_ctx=3, vpt_project=16, coop_n_ctx=4, B=2, C=5),
+    dict(name="tiny_vpt_deep_dropout", arch="tiny", vpt_n_ctx=4, vpt_deep=True, vpt_dropout=0.25, B=3, C=5),
+    dict(name="tiny_vpt_shallow_project_dropout", arch="tiny", vpt_n_ctx=3, vpt_project=16, vpt_dropout=0.5, B=4, C=5),
     dict(name="b16_coop_end", arch="ViT-B/16", coop_n_ctx=16, B=2, C=10),
     dict(name="b16_vpt_deep", arch="ViT-B/16", vpt_n_ctx=8, vpt_deep=True, B=2, C=10),
     dict(name="b16_upt_transformer", arch="ViT-B/16", coop_n_ctx=16, vpt_n_ctx=8, vpt_deep=True, position="middle",
@@ -140,7 +145,8 @@ def run_case(case, out_dir: Path):
     pp = synth.synth_prompt_params(case["arch"], case.get("coop_n_ctx", 0), case.get("vpt_n_ctx", 0),
                                    case.get("vpt_deep", False), csc_classes=C if case.get("csc") else 0,
                                    project_dim=case.get("project_dim", 0) if case.get("project_method") == "transformer" else 0,
-                                   seed=0, cocoop_n_ctx=case.get("cocoop_n_ctx", 0))
+                                   seed=0, cocoop_n_ctx=case.get("cocoop_n_ctx", 0),
+                                   vpt_project=case.get("vpt_project", -1))
     missing, unexpected = pl.load_state_dict(pp, strict=False)
     assert not unexpected, unexpected
     assert all(k in ("token_prefix", "token_suffix") for k in missing), missing
@@ -164,6 +170,12 @@ def run_case(case, out_dir: Path):
     else:
         label_in = label
 
+    # vpt_dropout (training mode): record the Bernoulli draws of the reference's own nn.Dropout, in call order
+    # (forward_vpt first, then one per deep layer), so that the oracle can be pinned with the masks given
+    drop_keep = []
+    if case.get("vpt_dropout"):
+        assert pl.vpt_dropout.training
+        pl.vpt_dropout.register_forward_hook(lambda m, inp, out: drop_keep.append((out != 0).detach().clone()))
     logits = model(image, task=task)
     lab = label_in
     if lab.dim() > 1:
@@ -182,7 +194,9 @@ def run_case(case, out_dir: Path):
         image_fingerprint=float(image.double().abs().sum()),
         torch_version=torch.__version__,
     )
-    if case["arch"] == "tiny":
+    if drop_keep:
+        fix["drop_keep"] = drop_keep
+    if case["arch"] == "tiny" and not case.get("vpt_dropout"):
         with torch.no_grad():
             ctx, vpt, vpt_deep = pl.forward_mvlpt_proj(torch.float32)
             fix["proj_ctx"], fix["proj_vpt"], fix["proj_vpt_deep"] = ctx, vpt, vpt_deep

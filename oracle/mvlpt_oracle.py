@@ -92,24 +92,38 @@ def patch_embed(image: Tensor, sd: Dict[str, Tensor]) -> Tensor:
 
 
 def image_tower(image: Tensor, sd: Dict[str, Tensor], vpt: Optional[Tensor] = None,
-                vpt_deep: Optional[Tensor] = None) -> Tensor:
-    """trainers/mvlpt.py:52-93 with forward_vpt (:416-437).  `vpt` [1,v,d]: rows inserted after the class token
-    (no positional embedding, no ln_pre).  `vpt_deep` [layers-1,v,d]: before block l>=1 rows 1..v are overwritten
+                vpt_deep: Optional[Tensor] = None, vpt_proj: Optional[Sequence[Tensor]] = None,
+                drop_p: float = 0.0, drop_keep: Optional[Sequence[Tensor]] = None) -> Tensor:
+    """trainers/mvlpt.py:52-93 with forward_vpt (:416-437).  `vpt` [1,v,p]: rows inserted after the class token
+    (no positional embedding, no ln_pre).  `vpt_deep` [layers-1,v,p]: before block l>=1 rows 1..v are overwritten
     with vpt_deep[l-1]; blocks with l > vpt_deep.shape[0] are SKIPPED (reference quirk, :73).
-    vpt_proj is Identity (VPT.PROJECT=-1 default) and vpt_dropout p=0."""
+    `vpt_proj` = (weight [d,p], bias [d]) of the Linear the reference builds when VPT.PROJECT > -1 (:170-175), applied
+    to each slab before the batch expansion (:76-77, :425); None = Identity (the default).
+    `drop_p`, `drop_keep`: vpt_dropout (:165) in training mode with the keep masks GIVEN — drop_keep[l] is a bool
+    [B,v,d] tensor for the slab entering block l (l=0: the shallow prompts): rows = slab * keep / (1 - p), exactly what
+    nn.Dropout computes once its Bernoulli draw is fixed."""
     heads = sd["visual.conv1.weight"].shape[0] // 64
     x = patch_embed(image, sd)
     B = x.shape[0]
     v = 0
+
+    def rows(slab: Tensor, l: int) -> Tensor:
+        if vpt_proj is not None:
+            slab = slab @ vpt_proj[0].to(slab.dtype).t() + vpt_proj[1].to(slab.dtype)
+        slab = slab.to(x.dtype).expand(B, -1, -1)
+        if drop_p > 0.0 and drop_keep is not None:
+            slab = slab * drop_keep[l].to(x.dtype) / (1.0 - drop_p)
+        return slab
+
     if vpt is not None:
         v = vpt.shape[1]
-        x = torch.cat([x[:, :1], vpt.to(x.dtype).expand(B, -1, -1), x[:, 1:]], dim=1)
+        x = torch.cat([x[:, :1], rows(vpt.reshape(v, -1), 0), x[:, 1:]], dim=1)
     layers = _n_layers(sd, "visual.")
     for l in range(layers):
         if vpt_deep is not None and l >= 1:
             if l > vpt_deep.shape[0]:
                 continue
-            x = torch.cat([x[:, :1], vpt_deep[l - 1].to(x.dtype).expand(B, -1, -1), x[:, 1 + v:]], dim=1)
+            x = torch.cat([x[:, :1], rows(vpt_deep[l - 1], l), x[:, 1 + v:]], dim=1)
         x = residual_block(x, sd, f"visual.transformer.resblocks.{l}.", heads, causal=False)
     c = layer_norm(x[:, 0], sd["visual.ln_post.weight"], sd["visual.ln_post.bias"])
     return c @ sd["visual.proj"].to(x.dtype)
@@ -254,13 +268,15 @@ def cocoop_logits(img_f: Tensor, sd: Dict[str, Tensor], pp: Dict[str, Tensor], e
 def custom_clip_forward(image: Tensor, sd: Dict[str, Tensor], pp: Dict[str, Tensor], embedding: Tensor,
                         eot_index: Tensor, name_lens: Sequence[int], n_ctx: int, v: int, position: str = "end",
                         upt: bool = False, task: Optional[Tensor] = None,
-                        task_ranges: Optional[Tensor] = None, cocoop_n_ctx: int = 0) -> Tensor:
+                        task_ranges: Optional[Tensor] = None, cocoop_n_ctx: int = 0, drop_p: float = 0.0,
+                        drop_keep: Optional[Sequence[Tensor]] = None) -> Tensor:
     """trainers/mvlpt.py:540-583: projection -> image tower -> prompt assembly -> text tower -> cosine logits
     (or, with COCOOP.N_CTX > 0, the instance-conditioned branch)."""
     ctx, vpt, vpt_deep = pp.get("ctx"), pp.get("vpt_embeddings"), pp.get("vpt_embeddings_deep")
     if upt and ctx is not None and vpt is not None:
         ctx, vpt, vpt_deep = upt_project(pp, n_ctx, v, dtype=image.dtype)
-    img_f = image_tower(image, sd, vpt, vpt_deep)
+    proj = (pp["vpt_proj.weight"], pp["vpt_proj.bias"]) if "vpt_proj.weight" in pp else None
+    img_f = image_tower(image, sd, vpt, vpt_deep, proj, drop_p, drop_keep)
     if cocoop_n_ctx:
         logits = cocoop_logits(img_f, sd, pp, embedding.to(image.dtype), eot_index, cocoop_n_ctx)
         if task is not None and task_ranges is not None:  # :573-581

@@ -27,7 +27,7 @@ def case_inputs(name: str):
     pp = synth.synth_prompt_params(case["arch"], case.get("coop_n_ctx", 0), case.get("vpt_n_ctx", 0),
                                    case.get("vpt_deep", False), csc_classes=case["C"] if case.get("csc") else 0,
                                    project_dim=case.get("project_dim", 0) if upt else 0, seed=0,
-                                   cocoop_n_ctx=case.get("cocoop_n_ctx", 0))
+                                   cocoop_n_ctx=case.get("cocoop_n_ctx", 0), vpt_project=case.get("vpt_project", -1))
     return fx, case, arch, sd, image, pp, upt
 
 
@@ -44,7 +44,8 @@ def make_cfg(case, prec="fp16"):
         TRAINER=NS(
             MVLPT=NS(PREC=prec, PROJECT_METHOD=case.get("project_method", "identity"),
                      PROJECT_DIM=case.get("project_dim", 128),
-                     VPT=NS(N_CTX=case.get("vpt_n_ctx", 0), CTX_INIT="", DROPOUT=0.0, PROJECT=-1,
+                     VPT=NS(N_CTX=case.get("vpt_n_ctx", 0), CTX_INIT="", DROPOUT=case.get("vpt_dropout", 0.0),
+                            PROJECT=case.get("vpt_project", -1),
                             DEEP=case.get("vpt_deep", False)),
                      COOP=NS(N_CTX=case.get("coop_n_ctx", 0), CTX_INIT="", CSC=case.get("csc", False),
                              CLASS_TOKEN_POSITION=case.get("position", "end")),
@@ -82,4 +83,5 @@ def oracle_kwargs(fx, case, sd, upt):
     emb = sd["token_embedding.weight"][fx["tokenized_prompts"]]
     return dict(embedding=emb, eot_index=fx["eot_index"], name_lens=fx["name_lens"], n_ctx=case.get("coop_n_ctx", 0),
                 v=case.get("vpt_n_ctx", 0), position=case.get("position", "end"), upt=upt, task=fx["task"],
-                task_ranges=fx["task_ranges"], cocoop_n_ctx=case.get("cocoop_n_ctx", 0))
+                task_ranges=fx["task_ranges"], cocoop_n_ctx=case.get("cocoop_n_ctx", 0),
+                drop_p=case.get("vpt_dropout", 0.0), drop_keep=fx.get("drop_keep"))

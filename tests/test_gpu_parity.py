@@ -16,7 +16,8 @@ LOGIT_TOL = 3e-3
 GRAD_TOL = 2e-2
 
 TINY = ["tiny_coop_end", "tiny_coop_middle_cut", "tiny_coop_front_csc", "tiny_vpt_shallow", "tiny_vpt_deep",
-        "tiny_vpt_deep_taskmask_soft", "tiny_upt_identity", "tiny_upt_transformer", "tiny_cocoop", "tiny_cocoop_vpt_deep"]
+        "tiny_vpt_deep_taskmask_soft", "tiny_upt_identity", "tiny_upt_transformer", "tiny_cocoop", "tiny_cocoop_vpt_deep",
+        "tiny_vpt_deep_project", "tiny_vpt_shallow_project_coop"]
 FULL = ["b16_coop_end", "b16_vpt_deep", "b16_upt_transformer", "b32_coop_cfg1", "l14_coop_end"]
 
 
@@ -164,3 +165,50 @@ def test_causal_cut_of_the_text_tower_changes_nothing(name, monkeypatch):
     for k in out["0"][1]:
         assert rel_err(out["1"][1][k], out["0"][1][k]) < 1e-6, k
     assert torch.equal(out["1"][2], out["0"][2]), "forward_coop (API parity, full length) differs"
+
+
+@pytest.mark.parametrize("prec", ["fp32", "fp16"])
+@pytest.mark.parametrize("name", ["tiny_vpt_deep_dropout", "tiny_vpt_shallow_project_dropout"])
+def test_vpt_dropout_training_step_matches_oracle_on_the_kernels_masks(name, prec):
+    """vpt_dropout in training mode (trainers/mvlpt.py:76,165,425).  The reference draws its masks from torch's RNG; the
+    oracle is pinned to it with those draws GIVEN (tests/test_oracle_golden.py, fixtures `drop_keep`).  Here the kernels
+    draw their own counter-based masks; mvlpt_dropout_keep returns them and the oracle replays the step with them."""
+    from oracle import mvlpt_oracle as O
+    from mvlpt_b200 import ops
+    from tests.helpers import build_custom_clip, oracle_kwargs, rel_err
+    model, fx, case, sd, image, pp, upt = build_custom_clip(name, prec)
+    pl = model.prompt_learner
+    p = case["vpt_dropout"]
+    assert pl.training and pl.vpt_dropout.p == p
+    pl.drop_seed_override = 20240229
+    img = image.cuda().half() if prec == "fp16" else image.cuda()
+    B, v = image.shape[0], case["vpt_n_ctx"]
+    d = model.image_encoder.tower(img.device).d
+    n_slabs = 1 + (pl.vpt_embeddings_deep.shape[0] if case.get("vpt_deep") else 0)
+    loss_rows, pred, grads = model.loss_and_grads(img, fx["label"].cuda(), fx["task"])
+    logits = model.last_logits(B).float().cpu()
+    keep = []
+    for slab in range(n_slabs):
+        k = torch.empty(B, v, d, dtype=torch.uint8, device="cuda")
+        ops.dropout_keep(k, B, v, d, p, pl.drop_seed_override, slab)
+        keep.append(k.bool().cpu())
+    rate = torch.stack(keep).float().mean().item()
+    n = torch.stack(keep).numel()
+    assert abs(rate - (1 - p)) < 5 * (p * (1 - p) / n) ** 0.5 + 1e-4, rate
+    if n_slabs > 1:
+        assert not torch.equal(keep[0], keep[1])
+    kw = oracle_kwargs(fx, case, sd, upt)
+    kw["drop_keep"] = keep
+    o_logits, o_loss, o_grads = O.train_step(image, fx["label"], sd, pp, **kw)
+    top2 = o_logits.topk(2, dim=-1).values
+    _check_against(o_logits, o_loss, o_grads, top2[:, 0] - top2[:, 1], logits, loss_rows.cpu(), pred.cpu(),
+                   {k: g.cpu() for k, g in grads.items()})
+    # another seed: another mask, other logits; eval mode: no dropout at all (nn.Dropout semantics)
+    pl.drop_seed_override = 7
+    model.loss_and_grads(img, fx["label"].cuda(), fx["task"])
+    assert not torch.equal(model.last_logits(B).float().cpu(), logits)
+    pl.eval()
+    kw["drop_p"], kw["drop_keep"] = 0.0, None
+    e_logits, _, _ = O.train_step(image, fx["label"], sd, pp, **kw)
+    model.loss_and_grads(img, fx["label"].cuda(), fx["task"])
+    assert rel_err(model.last_logits(B).float().cpu(), e_logits) <= LOGIT_TOL
