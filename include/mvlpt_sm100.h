@@ -215,6 +215,31 @@ int mvlpt_vpt_proj_bwd(const void* d_out, const void* emb, const void* W, int pa
                        int rows, int d, int p, int accumulate, mvlpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Input pipeline in front of the image tower: decoded uint8 RGB images -> the normalised batch.
+ * Replaces, bit for bit, the reference's CPU transforms: torchvision `Resize(SIZE, BICUBIC)` [+ `CenterCrop`] ->
+ * `ToTensor` -> `Normalize(PIXEL_MEAN, PIXEL_STD)` (trainers/vision_benchmark/evaluation/feature.py:540-553) and Dassl's
+ * `RandomResizedCrop` -> `RandomHorizontalFlip` -> ToTensor -> Normalize for configs/trainers/MVLPT/vit_b16.yaml:8-13,
+ * i.e. Pillow's two-pass fixed-point bicubic `Image.resize` (src/libImaging/Resample.c) on the crop box.
+ *   src: device buffer holding the images as uint8 [H, W, 3] rows packed, image b at byte offset descs[b].src_off.
+ *   descs: one descriptor per image, given BOTH as a host array (launch planning) and as a device copy (kernels).
+ *   out: [B, 3, out_h, out_w] fp32, or fp16 (fp32 result rounded to nearest) when out_f16; out_w <= 256.
+ *   mean3 / std3: host pointers to 3 floats.  workspace: mvlpt_preprocess_workspace(...) bytes of device memory.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t src_off;   /* byte offset of pixel (0,0) of this image in src                                   */
+    int H, W;           /* decoded size                                                                      */
+    int by, bx, bh, bw; /* crop box (top, left, height, width) taken BEFORE resizing; whole image = 0,0,H,W   */
+    int rh, rw;         /* size the box is resized to                                                        */
+    int oy, ox;         /* top-left of the out_h x out_w window kept from the resized box (CenterCrop); else 0 */
+    int flip;           /* horizontal flip of the window                                                     */
+} mvlpt_image_desc;
+
+size_t mvlpt_preprocess_workspace(const mvlpt_image_desc* descs_host, int B, int out_h, int out_w);
+int mvlpt_preprocess(const void* src, const mvlpt_image_desc* descs_host, const mvlpt_image_desc* descs_dev, int B,
+                     const float* mean3, const float* std3, void* out, int out_f16, int out_h, int out_w, void* workspace,
+                     size_t ws_bytes, mvlpt_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * CoCoOp branch (trainers/mvlpt.py:260-290 meta_net, :348-374 forward_cocoop, :556-571 per-image text features).
  * The text tower itself runs the usual kernels on B*C sequences; these are the pieces around it (fp32 arithmetic;
  * parameters fp16 or fp32 by param_f16 / ctx_f16).

@@ -1,0 +1,231 @@
+// Input pipeline in front of the image tower: decoded uint8 HWC images -> the normalised [B,3,S,S]
+// batch, on the GPU, BIT-IDENTICAL to what the reference's CPU pipeline produces:
+//   torchvision (Random)ResizedCrop / Resize [+ CenterCrop] with BICUBIC over Pillow -> RandomHorizontalFlip -> ToTensor ->
+//   Normalize   (trainers/vision_benchmark/evaluation/feature.py:540-553; dassl build_transform for
+//   configs/trainers/MVLPT/vit_b16.yaml:8-13).
+// Pillow's Image.resize (src/libImaging/Resample.c, 8-bit path) is a separable two-pass convolution — horizontal first,
+// uint8 intermediate — with double-precision bicubic (a = -0.5) coefficients whose support grows with the down-scaling
+// factor, normalised, turned into 22-bit fixed point, accumulated in int32 with a rounding constant, shifted and clipped.
+// Three kernels: (1) coefficient tables per image and axis, in fp64 with every operation individually rounded (no FMA
+// contraction: the tables must equal what x86-64 Pillow computes), (2) horizontal pass box -> uint8 [bh, S_w, 3],
+// (3) vertical pass + /255 + (x - mean)/std (IEEE fp32 division, as torch does) + flip + NCHW store (fp32 or fp16).
+// HBM-bound byte work ("at 10 k+ img/s the CPU PIL/bicubic loader becomes the bottleneck").
+#include "common.cuh"
+#include <cuda_fp16.h>
+
+using namespace mvlpt;
+
+namespace {
+
+constexpr int kPrecisionBits = 32 - 8 - 2;
+
+__device__ __forceinline__ double bicubic_w(double x) {
+    // ((a + 2) x - (a + 3)) x x + 1  |  (((x - 5) x + 8) x - 4) a   with a = -0.5, evaluated in Pillow's operation order
+    if (x < 0.0) x = -x;
+    if (x < 1.0) return __dadd_rn(__dmul_rn(__dmul_rn(__dsub_rn(__dmul_rn(1.5, x), 2.5), x), x), 1.0);
+    if (x < 2.0) return __dmul_rn(__dsub_rn(__dmul_rn(__dadd_rn(__dmul_rn(__dsub_rn(x, 5.0), x), 8.0), x), 4.0), -0.5);
+    return 0.0;
+}
+
+struct Axis {
+    int in_size, out_size, win0, win;  // resize in_size -> out_size, keep outputs [win0, win0 + win)
+};
+__device__ __forceinline__ Axis axis_of(const mvlpt_image_desc& d, int axis, int out_h, int out_w) {
+    return axis == 0 ? Axis{d.bw, d.rw, d.ox, out_w} : Axis{d.bh, d.rh, d.oy, out_h};
+}
+
+// tables for image b, axis a: bounds[(b*2+a)*S + i] = (first tap, tap count); kk[((b*2+a)*K + t)*S + i] (tap-major so that
+// neighbouring outputs read neighbouring words).  S = max(out_h, out_w), K = max taps over the batch.
+__global__ void coeff_kernel(const mvlpt_image_desc* __restrict__ descs, int B, int out_h, int out_w, int S, int K,
+                             int2* __restrict__ bounds, int* __restrict__ kk) {
+    const int b = blockIdx.y >> 1, a = blockIdx.y & 1;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const Axis ax = axis_of(descs[b], a, out_h, out_w);
+    if (i >= ax.win) return;
+    const int xx = ax.win0 + i;
+    const double scale = __ddiv_rn((double)ax.in_size, (double)ax.out_size);
+    const double filterscale = scale < 1.0 ? 1.0 : scale;
+    const double support = __dmul_rn(2.0, filterscale);
+    const double ss = __ddiv_rn(1.0, filterscale);
+    const double center = __dmul_rn(__dadd_rn((double)xx, 0.5), scale);
+    int xmin = __double2int_rz(__dadd_rn(__dsub_rn(center, support), 0.5));
+    if (xmin < 0) xmin = 0;
+    int xmax = __double2int_rz(__dadd_rn(__dadd_rn(center, support), 0.5));
+    if (xmax > ax.in_size) xmax = ax.in_size;
+    const int n = xmax - xmin;
+    double ww = 0.0;
+    for (int x = 0; x < n; ++x)
+        ww = __dadd_rn(ww, bicubic_w(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss)));
+    int* k = kk + (size_t)(b * 2 + a) * K * S + i;
+    for (int x = 0; x < K; ++x) {
+        int q = 0;
+        if (x < n) {
+            double w = bicubic_w(__dmul_rn(__dadd_rn(__dsub_rn((double)(x + xmin), center), 0.5), ss));
+            if (ww != 0.0) w = __ddiv_rn(w, ww);
+            const double f = __dmul_rn(w, (double)(1 << kPrecisionBits));
+            q = __double2int_rz(w < 0.0 ? __dadd_rn(-0.5, f) : __dadd_rn(0.5, f));
+        }
+        k[(size_t)x * S] = q;
+    }
+    bounds[(size_t)(b * 2 + a) * S + i] = make_int2(xmin, n);
+}
+
+__device__ __forceinline__ int clip8(int acc) {
+    const int v = acc >> kPrecisionBits;  // arithmetic shift, then clamp (Resample.c clip8 lookup)
+    return v < 0 ? 0 : (v > 255 ? 255 : v);
+}
+
+// horizontal pass: tmp[b][y][i][c] for y in [0, bh), i in [0, out_w).  Block = one image, kRows source rows at a time, each
+// staged in shared memory; thread = one output column.
+constexpr int kRowsPerBlock = 8;
+__global__ void __launch_bounds__(256)
+hpass_kernel(const unsigned char* __restrict__ src, const mvlpt_image_desc* __restrict__ descs, int out_w, int S, int K,
+             const int2* __restrict__ bounds, const int* __restrict__ kk, unsigned char* __restrict__ tmp,
+             size_t tmp_stride) {
+    extern __shared__ unsigned char row[];
+    const int b = blockIdx.y;
+    const mvlpt_image_desc d = descs[b];
+    const int y0 = blockIdx.x * kRowsPerBlock;
+    if (y0 >= d.bh) return;
+    const int2 bd = threadIdx.x < out_w ? bounds[(size_t)(b * 2) * S + threadIdx.x] : make_int2(0, 0);
+    const int* k = kk + (size_t)(b * 2) * K * S + threadIdx.x;
+    const int nbytes = d.bw * 3;
+    for (int y = y0; y < min(y0 + kRowsPerBlock, d.bh); ++y) {
+        const unsigned char* s = src + d.src_off + ((size_t)(d.by + y) * d.W + d.bx) * 3;
+        __syncthreads();
+        for (int i = threadIdx.x; i < nbytes; i += blockDim.x) row[i] = __ldg(s + i);
+        __syncthreads();
+        if (threadIdx.x < out_w) {
+            int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+            const unsigned char* p = row + bd.x * 3;
+            for (int t = 0; t < bd.y; ++t) {
+                const int w = k[(size_t)t * S];
+                a0 += p[3 * t] * w; a1 += p[3 * t + 1] * w; a2 += p[3 * t + 2] * w;
+            }
+            unsigned char* o = tmp + (size_t)b * tmp_stride + ((size_t)y * out_w + threadIdx.x) * 3;
+            o[0] = (unsigned char)clip8(a0); o[1] = (unsigned char)clip8(a1); o[2] = (unsigned char)clip8(a2);
+        }
+    }
+}
+
+struct Norm {
+    float mean[3], std[3];
+};
+template <typename T> __device__ __forceinline__ T cvt_out(float v);
+template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
+template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
+
+// vertical pass + ToTensor + Normalize + flip: out[b][c][yo][flip ? out_w-1-i : i]
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+vpass_kernel(const mvlpt_image_desc* __restrict__ descs, int out_h, int out_w, int S, int K, const int2* __restrict__ bounds,
+             const int* __restrict__ kk, const unsigned char* __restrict__ tmp, size_t tmp_stride, Norm nm,
+             OutT* __restrict__ out) {
+    const int b = blockIdx.y;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= out_h * out_w) return;
+    const int yo = idx / out_w, i = idx % out_w;
+    const int2 bd = bounds[(size_t)(b * 2 + 1) * S + yo];
+    const int* k = kk + (size_t)(b * 2 + 1) * K * S + yo;
+    const unsigned char* p = tmp + (size_t)b * tmp_stride + ((size_t)bd.x * out_w + i) * 3;
+    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+    for (int t = 0; t < bd.y; ++t) {
+        const int w = k[(size_t)t * S];
+        const unsigned char* q = p + (size_t)t * out_w * 3;
+        a0 += q[0] * w; a1 += q[1] * w; a2 += q[2] * w;
+    }
+    const int px[3] = {clip8(a0), clip8(a1), clip8(a2)};
+    const int xo = descs[b].flip ? out_w - 1 - i : i;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float x = __fdiv_rn((float)px[c], 255.f);
+        const float v = __fdiv_rn(__fsub_rn(x, nm.mean[c]), nm.std[c]);
+        out[(((size_t)b * 3 + c) * out_h + yo) * out_w + xo] = cvt_out<OutT>(v);
+    }
+}
+
+struct Plan {
+    int S, K, max_bh, max_bw;
+    size_t off_bounds, off_kk, off_tmp, tmp_stride, total;
+};
+
+int taps(int in_size, int out_size) {  // ksize of Resample.c precompute_coeffs
+    double fs = (double)in_size / out_size;
+    if (fs < 1.0) fs = 1.0;
+    return (int)ceil(2.0 * fs) * 2 + 1;
+}
+
+int make_plan(const mvlpt_image_desc* h, int B, int out_h, int out_w, Plan& p, const char* who) {
+    if (!h) return fail(MVLPT_EINVAL, "%s: null descriptors", who);
+    if (B <= 0 || out_h <= 0 || out_w <= 0 || out_w > 256)
+        return fail(MVLPT_EINVAL, "%s: need B > 0 and 0 < out_w <= 256, out_h > 0", who);
+    p.S = out_h > out_w ? out_h : out_w;
+    p.K = 1; p.max_bh = 1; p.max_bw = 1;
+    for (int b = 0; b < B; ++b) {
+        const mvlpt_image_desc& d = h[b];
+        if (d.H <= 0 || d.W <= 0 || d.bh <= 0 || d.bw <= 0 || d.by < 0 || d.bx < 0 || d.by + d.bh > d.H || d.bx + d.bw > d.W)
+            return fail(MVLPT_ESHAPE, "%s: image %d: crop box outside the %dx%d image", who, b, d.H, d.W);
+        if (d.rh <= 0 || d.rw <= 0 || d.oy < 0 || d.ox < 0 || d.oy + out_h > d.rh || d.ox + out_w > d.rw)
+            return fail(MVLPT_ESHAPE, "%s: image %d: output window outside the resized %dx%d image", who, b, d.rh, d.rw);
+        const int kx = taps(d.bw, d.rw), ky = taps(d.bh, d.rh);
+        if (kx > p.K) p.K = kx;
+        if (ky > p.K) p.K = ky;
+        if (d.bh > p.max_bh) p.max_bh = d.bh;
+        if (d.bw > p.max_bw) p.max_bw = d.bw;
+    }
+    if ((size_t)p.max_bw * 3 > 200 * 1024) return fail(MVLPT_ESHAPE, "%s: crop rows wider than 68k pixels are not supported", who);
+    auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
+    size_t o = 0;
+    p.off_bounds = o; o = up(o + (size_t)B * 2 * p.S * sizeof(int2));
+    p.off_kk = o;     o = up(o + (size_t)B * 2 * p.K * p.S * sizeof(int));
+    p.tmp_stride = up((size_t)p.max_bh * out_w * 3);
+    p.off_tmp = o;    o = up(o + (size_t)B * p.tmp_stride);
+    p.total = o;
+    return MVLPT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+size_t mvlpt_preprocess_workspace(const mvlpt_image_desc* descs_host, int B, int out_h, int out_w) {
+    Plan p;
+    if (make_plan(descs_host, B, out_h, out_w, p, "mvlpt_preprocess_workspace")) return 0;
+    return p.total;
+}
+
+int mvlpt_preprocess(const void* src, const mvlpt_image_desc* descs_host, const mvlpt_image_desc* descs_dev, int B,
+                     const float* mean3, const float* std3, void* out, int out_f16, int out_h, int out_w, void* workspace,
+                     size_t ws_bytes, mvlpt_stream_t stream) {
+    if (!src || !descs_dev || !mean3 || !std3 || !out || !workspace) return fail(MVLPT_EINVAL, "mvlpt_preprocess: null argument");
+    Plan p;
+    int rc = make_plan(descs_host, B, out_h, out_w, p, "mvlpt_preprocess");
+    if (rc) return rc;
+    if (ws_bytes < p.total) return fail(MVLPT_EINVAL, "mvlpt_preprocess: workspace too small (%zu < %zu)", ws_bytes, p.total);
+    if ((rc = require_sm100())) return rc;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* ws = static_cast<char*>(workspace);
+    int2* bounds = reinterpret_cast<int2*>(ws + p.off_bounds);
+    int* kk = reinterpret_cast<int*>(ws + p.off_kk);
+    unsigned char* tmp = reinterpret_cast<unsigned char*>(ws + p.off_tmp);
+    coeff_kernel<<<dim3(cdiv(p.S, 128), 2 * B), 128, 0, s>>>(descs_dev, B, out_h, out_w, p.S, p.K, bounds, kk);
+    if ((rc = launched("preprocess coeff"))) return rc;
+    const size_t smem = ((size_t)p.max_bw * 3 + 15) & ~size_t(15);
+    if (smem > 48 * 1024)
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(hpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    hpass_kernel<<<dim3(cdiv(p.max_bh, kRowsPerBlock), B), 256, smem, s>>>(
+        static_cast<const unsigned char*>(src), descs_dev, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride);
+    if ((rc = launched("preprocess hpass"))) return rc;
+    Norm nm;
+    for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3[c]; nm.std[c] = std3[c]; }
+    const dim3 grid(cdiv(out_h * out_w, 256), B);
+    if (out_f16)
+        vpass_kernel<__half><<<grid, 256, 0, s>>>(descs_dev, out_h, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride, nm,
+                                                  static_cast<__half*>(out));
+    else
+        vpass_kernel<float><<<grid, 256, 0, s>>>(descs_dev, out_h, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride, nm,
+                                                 static_cast<float*>(out));
+    return launched("preprocess vpass");
+}
+
+}  // extern "C"

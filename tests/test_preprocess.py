@@ -1,0 +1,75 @@
+"""Input pipeline, CPU side: the oracle's restatement of Pillow's bicubic resize + torchvision's
+ToTensor/Normalize/crop-box draws is pinned BIT-EXACTLY to Pillow + torchvision themselves (both ship in this image) and
+to the committed fixture tests/golden/preprocess.pt (oracle/gen_golden_preprocess.py); the host-side geometry of
+mvlpt_b200.input_pipeline makes the same random draws as torchvision."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import preprocess_oracle as P
+from tests.conftest import load_golden
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return load_golden("preprocess")
+
+
+def _oracle_case(img, mode, size, mean, std):
+    if mode == "stretch":
+        u8 = P.resize_bicubic(img, size[0], size[1])
+    else:
+        u8 = P.resize_center_crop(img, size)
+    return P.to_tensor_normalize(u8, mean, std)
+
+
+def test_oracle_matches_golden_bit_exact(golden):
+    imgs = [t.numpy() for t in golden["images"]]
+    for case in golden["cases"]:
+        out = _oracle_case(imgs[case["image"]], case["mode"], golden["size"], golden["mean"], golden["std"])
+        assert np.array_equal(out, case["tensor"].numpy()), (case["image"], case["mode"])
+
+
+def test_geometry_draws_and_oracle_reproduce_the_seeded_train_stack(golden):
+    """RandomResizedCrop + RandomHorizontalFlip: same torch seed -> same boxes/flips -> bit-identical tensors."""
+    from mvlpt_b200.input_pipeline import GpuTransform
+    tf = GpuTransform(golden["size"], golden["mean"], golden["std"], "train")
+    torch.manual_seed(golden["train_seed"])
+    for img, ref in zip(golden["images"], golden["train"]):
+        a = img.numpy()
+        box, (rh, rw), (oy, ox), flip = tf.geometry(a.shape[0], a.shape[1])
+        assert (rh, rw) == tuple(golden["size"]) and (oy, ox) == (0, 0)
+        out = P.to_tensor_normalize(P.resized_crop(a, box, golden["size"], bool(flip)), golden["mean"], golden["std"])
+        assert np.array_equal(out, ref.numpy())
+
+
+def test_crop_params_equal_torchvision_draw_for_draw():
+    import torchvision.transforms as T
+    from mvlpt_b200.input_pipeline import random_resized_crop_params
+    for seed, (h, w) in enumerate([(375, 500), (224, 224), (31, 900), (1200, 40), (8, 8)]):
+        torch.manual_seed(seed)
+        ref = [T.RandomResizedCrop.get_params(torch.empty(3, h, w), [0.08, 1.0], [3 / 4, 4 / 3]) for _ in range(20)]
+        tail_ref = torch.rand(1)
+        torch.manual_seed(seed)
+        ours = [random_resized_crop_params(h, w) for _ in range(20)]
+        assert ours == [tuple(r) for r in ref]
+        assert torch.equal(torch.rand(1), tail_ref)  # consumed exactly the same number of draws
+
+
+@pytest.mark.parametrize("shape,out", [((37, 53), (24, 24)), ((300, 200), (224, 224)), ((20, 30), (64, 48)),
+                                       ((224, 224), (224, 224)), ((375, 500), (224, 224)), ((64, 64), (224, 224)),
+                                       ((7, 9), (32, 32)), ((700, 31), (40, 40)), ((1, 1), (16, 16))])
+def test_oracle_resize_equals_pillow_live(shape, out):
+    from PIL import Image
+    g = np.random.default_rng(shape[0] * 1000 + shape[1])
+    img = g.integers(0, 256, (*shape, 3), dtype=np.uint8)
+    ref = np.asarray(Image.fromarray(img).resize((out[1], out[0]), Image.BICUBIC))
+    assert np.array_equal(P.resize_bicubic(img, out[0], out[1]), ref)
+
+
+def test_coefficients_are_a_partition_of_unity():
+    """Every row of fixed-point taps sums to 2^22 within the rounding of its entries; bounds stay inside the axis."""
+    for in_size, out_size in [(500, 224), (224, 224), (100, 224), (3, 7), (1000, 3)]:
+        bounds, kk = P.precompute_coeffs(in_size, out_size)
+        assert (bounds[:, 0] >= 0).all() and (bounds[:, 0] + bounds[:, 1] <= in_size).all()
+        assert np.abs(kk.sum(1) - (1 << P.PRECISION_BITS)).max() <= kk.shape[1]
