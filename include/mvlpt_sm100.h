@@ -220,7 +220,8 @@ int mvlpt_vpt_proj_bwd(const void* d_out, const void* emb, const void* W, int pa
  * `ToTensor` -> `Normalize(PIXEL_MEAN, PIXEL_STD)` (trainers/vision_benchmark/evaluation/feature.py:540-553) and Dassl's
  * `RandomResizedCrop` -> `RandomHorizontalFlip` -> ToTensor -> Normalize for configs/trainers/MVLPT/vit_b16.yaml:8-13,
  * i.e. Pillow's two-pass fixed-point bicubic `Image.resize` (src/libImaging/Resample.c) on the crop box.
- *   src: device buffer holding the images as uint8 [H, W, 3] rows packed, image b at byte offset descs[b].src_off.
+ *   src: device buffer holding the images as uint8 [H, W, 3] rows packed, image b at byte offset descs[b].src_off;
+ *     16-byte aligned and readable up to the next multiple of 16 behind every image (rows are fetched as aligned uint4).
  *   descs: one descriptor per image, given BOTH as a host array (launch planning) and as a device copy (kernels).
  *   out: [B, 3, out_h, out_w] fp32, or fp16 (fp32 result rounded to nearest) when out_f16; out_w <= 256.
  *   mean3 / std3: host pointers to 3 floats.  workspace: mvlpt_preprocess_workspace(...) bytes of device memory.

@@ -75,35 +75,58 @@ __device__ __forceinline__ int clip8(int acc) {
     return v < 0 ? 0 : (v > 255 ? 255 : v);
 }
 
-// horizontal pass: tmp[b][y][i][c] for y in [0, bh), i in [0, out_w).  Block = one image, kRows source rows at a time, each
-// staged in shared memory; thread = one output column.
+// horizontal pass: tmp[b][y][i][c] for y in [0, bh), i in [0, out_w).  Block = kRowsPerBlock source rows of one image,
+// staged in shared memory with aligned 16-byte loads (each row keeps its own misalignment); thread = one output column,
+// all rows at once, so every tap weight is loaded once per block.
 constexpr int kRowsPerBlock = 8;
 __global__ void __launch_bounds__(256)
 hpass_kernel(const unsigned char* __restrict__ src, const mvlpt_image_desc* __restrict__ descs, int out_w, int S, int K,
              const int2* __restrict__ bounds, const int* __restrict__ kk, unsigned char* __restrict__ tmp,
-             size_t tmp_stride) {
-    extern __shared__ unsigned char row[];
+             size_t tmp_stride, int row_stride) {
+    extern __shared__ __align__(16) unsigned char rows[];
     const int b = blockIdx.y;
     const mvlpt_image_desc d = descs[b];
     const int y0 = blockIdx.x * kRowsPerBlock;
     if (y0 >= d.bh) return;
-    const int2 bd = threadIdx.x < out_w ? bounds[(size_t)(b * 2) * S + threadIdx.x] : make_int2(0, 0);
-    const int* k = kk + (size_t)(b * 2) * K * S + threadIdx.x;
+    const int nrows = min(kRowsPerBlock, d.bh - y0);
     const int nbytes = d.bw * 3;
-    for (int y = y0; y < min(y0 + kRowsPerBlock, d.bh); ++y) {
-        const unsigned char* s = src + d.src_off + ((size_t)(d.by + y) * d.W + d.bx) * 3;
-        __syncthreads();
-        for (int i = threadIdx.x; i < nbytes; i += blockDim.x) row[i] = __ldg(s + i);
-        __syncthreads();
-        if (threadIdx.x < out_w) {
-            int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
-            const unsigned char* p = row + bd.x * 3;
-            for (int t = 0; t < bd.y; ++t) {
-                const int w = k[(size_t)t * S];
-                a0 += p[3 * t] * w; a1 += p[3 * t + 1] * w; a2 += p[3 * t + 2] * w;
+    int mis[kRowsPerBlock];
+#pragma unroll
+    for (int r = 0; r < kRowsPerBlock; ++r) {
+        mis[r] = 0;
+        if (r < nrows) {
+            const unsigned char* g = src + d.src_off + ((size_t)(d.by + y0 + r) * d.W + d.bx) * 3;
+            const int m = (int)(reinterpret_cast<size_t>(g) & 15);
+            mis[r] = m;
+            const uint4* ga = reinterpret_cast<const uint4*>(g - m);
+            uint4* sa = reinterpret_cast<uint4*>(rows + (size_t)r * row_stride);
+            for (int v = threadIdx.x; v * 16 < m + nbytes; v += blockDim.x) sa[v] = __ldg(ga + v);
+        }
+    }
+    __syncthreads();
+    const int i = threadIdx.x;
+    if (i >= out_w) return;
+    const int2 bd = bounds[(size_t)(b * 2) * S + i];
+    const int* k = kk + (size_t)(b * 2) * K * S + i;
+    int acc[kRowsPerBlock][3];
+#pragma unroll
+    for (int r = 0; r < kRowsPerBlock; ++r) acc[r][0] = acc[r][1] = acc[r][2] = 1 << (kPrecisionBits - 1);
+    for (int t = 0; t < bd.y; ++t) {
+        const int w = k[(size_t)t * S];
+        const int o = (bd.x + t) * 3;
+#pragma unroll
+        for (int r = 0; r < kRowsPerBlock; ++r) {
+            if (r < nrows) {
+                const unsigned char* p = rows + (size_t)r * row_stride + mis[r] + o;
+                acc[r][0] += p[0] * w; acc[r][1] += p[1] * w; acc[r][2] += p[2] * w;
             }
-            unsigned char* o = tmp + (size_t)b * tmp_stride + ((size_t)y * out_w + threadIdx.x) * 3;
-            o[0] = (unsigned char)clip8(a0); o[1] = (unsigned char)clip8(a1); o[2] = (unsigned char)clip8(a2);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < kRowsPerBlock; ++r) {
+        if (r < nrows) {
+            unsigned char* o = tmp + (size_t)b * tmp_stride + ((size_t)(y0 + r) * out_w + i) * 3;
+            o[0] = (unsigned char)clip8(acc[r][0]); o[1] = (unsigned char)clip8(acc[r][1]); o[2] = (unsigned char)clip8(acc[r][2]);
         }
     }
 }
@@ -115,32 +138,48 @@ template <typename T> __device__ __forceinline__ T cvt_out(float v);
 template <> __device__ __forceinline__ float cvt_out<float>(float v) { return v; }
 template <> __device__ __forceinline__ __half cvt_out<__half>(float v) { return __float2half_rn(v); }
 
-// vertical pass + ToTensor + Normalize + flip: out[b][c][yo][flip ? out_w-1-i : i]
-template <typename OutT>
+// vertical pass + ToTensor + Normalize + flip: out[b][c][yo][flip ? out_w-1-i : i].  Thread = 4 neighbouring output columns
+// of one row (12 contiguous bytes of every intermediate row = three aligned words when out_w % 4 == 0).
+template <typename OutT, bool VEC4>
 __global__ void __launch_bounds__(256)
 vpass_kernel(const mvlpt_image_desc* __restrict__ descs, int out_h, int out_w, int S, int K, const int2* __restrict__ bounds,
              const int* __restrict__ kk, const unsigned char* __restrict__ tmp, size_t tmp_stride, Norm nm,
              OutT* __restrict__ out) {
+    constexpr int P = VEC4 ? 4 : 1;
     const int b = blockIdx.y;
+    const int wq = out_w / P;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= out_h * out_w) return;
-    const int yo = idx / out_w, i = idx % out_w;
+    if (idx >= out_h * wq) return;
+    const int yo = idx / wq, i0 = (idx % wq) * P;
     const int2 bd = bounds[(size_t)(b * 2 + 1) * S + yo];
     const int* k = kk + (size_t)(b * 2 + 1) * K * S + yo;
-    const unsigned char* p = tmp + (size_t)b * tmp_stride + ((size_t)bd.x * out_w + i) * 3;
-    int a0 = 1 << (kPrecisionBits - 1), a1 = a0, a2 = a0;
+    const unsigned char* p = tmp + (size_t)b * tmp_stride + ((size_t)bd.x * out_w + i0) * 3;
+    int acc[P * 3];
+#pragma unroll
+    for (int j = 0; j < P * 3; ++j) acc[j] = 1 << (kPrecisionBits - 1);
     for (int t = 0; t < bd.y; ++t) {
         const int w = k[(size_t)t * S];
         const unsigned char* q = p + (size_t)t * out_w * 3;
-        a0 += q[0] * w; a1 += q[1] * w; a2 += q[2] * w;
+        if (VEC4) {
+            const uint32_t* q4 = reinterpret_cast<const uint32_t*>(q);
+            const uint32_t u[3] = {__ldg(q4), __ldg(q4 + 1), __ldg(q4 + 2)};
+#pragma unroll
+            for (int j = 0; j < 12; ++j) acc[j] += (int)((u[j >> 2] >> (8 * (j & 3))) & 0xFFu) * w;
+        } else {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) acc[j] += q[j] * w;
+        }
     }
-    const int px[3] = {clip8(a0), clip8(a1), clip8(a2)};
-    const int xo = descs[b].flip ? out_w - 1 - i : i;
+    const int flip = descs[b].flip;
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float x = __fdiv_rn((float)px[c], 255.f);
-        const float v = __fdiv_rn(__fsub_rn(x, nm.mean[c]), nm.std[c]);
-        out[(((size_t)b * 3 + c) * out_h + yo) * out_w + xo] = cvt_out<OutT>(v);
+        OutT* o = out + (((size_t)b * 3 + c) * out_h + yo) * out_w;
+#pragma unroll
+        for (int j = 0; j < P; ++j) {
+            const float x = __fdiv_rn((float)clip8(acc[j * 3 + c]), 255.f);
+            const float v = __fdiv_rn(__fsub_rn(x, nm.mean[c]), nm.std[c]);
+            o[flip ? out_w - 1 - (i0 + j) : i0 + j] = cvt_out<OutT>(v);
+        }
     }
 }
 
@@ -173,7 +212,6 @@ int make_plan(const mvlpt_image_desc* h, int B, int out_h, int out_w, Plan& p, c
         if (d.bh > p.max_bh) p.max_bh = d.bh;
         if (d.bw > p.max_bw) p.max_bw = d.bw;
     }
-    if ((size_t)p.max_bw * 3 > 200 * 1024) return fail(MVLPT_ESHAPE, "%s: crop rows wider than 68k pixels are not supported", who);
     auto up = [](size_t x) { return (x + 255) & ~size_t(255); };
     size_t o = 0;
     p.off_bounds = o; o = up(o + (size_t)B * 2 * p.S * sizeof(int2));
@@ -210,21 +248,24 @@ int mvlpt_preprocess(const void* src, const mvlpt_image_desc* descs_host, const 
     unsigned char* tmp = reinterpret_cast<unsigned char*>(ws + p.off_tmp);
     coeff_kernel<<<dim3(cdiv(p.S, 128), 2 * B), 128, 0, s>>>(descs_dev, B, out_h, out_w, p.S, p.K, bounds, kk);
     if ((rc = launched("preprocess coeff"))) return rc;
-    const size_t smem = ((size_t)p.max_bw * 3 + 15) & ~size_t(15);
+    const int row_stride = (int)((((size_t)p.max_bw * 3 + 15) & ~size_t(15)) + 16);  // + the row's own misalignment
+    const size_t smem = (size_t)row_stride * kRowsPerBlock;
+    if (smem > 200 * 1024) return fail(MVLPT_ESHAPE, "mvlpt_preprocess: crop rows of %d pixels do not fit shared memory", p.max_bw);
     if (smem > 48 * 1024)
         MVLPT_CUDA_OK(cudaFuncSetAttribute(hpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     hpass_kernel<<<dim3(cdiv(p.max_bh, kRowsPerBlock), B), 256, smem, s>>>(
-        static_cast<const unsigned char*>(src), descs_dev, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride);
+        static_cast<const unsigned char*>(src), descs_dev, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride, row_stride);
     if ((rc = launched("preprocess hpass"))) return rc;
     Norm nm;
     for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3[c]; nm.std[c] = std3[c]; }
-    const dim3 grid(cdiv(out_h * out_w, 256), B);
-    if (out_f16)
-        vpass_kernel<__half><<<grid, 256, 0, s>>>(descs_dev, out_h, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride, nm,
-                                                  static_cast<__half*>(out));
-    else
-        vpass_kernel<float><<<grid, 256, 0, s>>>(descs_dev, out_h, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride, nm,
-                                                 static_cast<float*>(out));
+    const bool vec4 = out_w % 4 == 0;
+    const dim3 grid(cdiv(out_h * (vec4 ? out_w / 4 : out_w), 256), B);
+#define MVLPT_VPASS(T, V)                                                                                              \
+    vpass_kernel<T, V><<<grid, 256, 0, s>>>(descs_dev, out_h, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride, nm,    \
+                                            static_cast<T*>(out))
+    if (out_f16) { if (vec4) MVLPT_VPASS(__half, true); else MVLPT_VPASS(__half, false); }
+    else         { if (vec4) MVLPT_VPASS(float, true);  else MVLPT_VPASS(float, false); }
+#undef MVLPT_VPASS
     return launched("preprocess vpass");
 }
 

@@ -124,11 +124,14 @@ class GpuTransform:
         head = (desc_bytes + 255) & ~255
         descs = (ImageDesc * B)()
         off = head
+        boxes = []
         for b, a in enumerate(arrs):
             H, W = a.shape[:2]
             (by, bx, bh, bw), (rh, rw), (oy, ox), flip = self.geometry(H, W)
-            descs[b] = ImageDesc(off, H, W, by, bx, bh, bw, rh, rw, oy, ox, flip)
-            off += (a.size + 15) & ~15
+            # only the crop box crosses PCIe: it is staged as an image of its own (the filter never looks outside it)
+            boxes.append(a[by:by + bh, bx:bx + bw])
+            descs[b] = ImageDesc(off, bh, bw, 0, 0, bh, bw, rh, rw, oy, ox, flip)
+            off += (bh * bw * 3 + 15) & ~15
         total = off
         if self._stage is None or self._stage.numel() < total:
             self._stage = torch.empty(int(total * 1.25), dtype=torch.uint8).pin_memory()
@@ -137,9 +140,9 @@ class GpuTransform:
             self._copied.synchronize()  # the previous batch has left the pinned staging buffer
         st = self._stage.numpy()
         st[:desc_bytes] = np.frombuffer(descs, dtype=np.uint8)
-        for b, a in enumerate(arrs):
+        for b, a in enumerate(boxes):
             o = descs[b].src_off
-            st[o:o + a.size] = a.reshape(-1)
+            st[o:o + a.size].reshape(a.shape)[...] = a
         self._dev[:total].copy_(self._stage[:total], non_blocking=True)
         self._copied = torch.cuda.Event()
         self._copied.record(torch.cuda.current_stream(self.device))
