@@ -19,11 +19,18 @@ if [[ $what == *bench* ]]; then
   echo "bench vpt exit $?"; cut -c1-900 gpurun_out/bench_vpt.json
   timeout 600 python bench.py --mode upt --classes 1000 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_upt.json 2> gpurun_out/bench_upt.err
   echo "bench upt exit $?"; cut -c1-900 gpurun_out/bench_upt.json
+  timeout 600 python bench.py --mode cocoop --batch 32 --classes 100 --steps 10 --warmup 3 --no-cpu-baseline > gpurun_out/bench_cocoop.json 2> gpurun_out/bench_cocoop.err
+  echo "bench cocoop exit $?"; cut -c1-600 gpurun_out/bench_cocoop.json
+  timeout 300 python tools/gpu_preprocess_bench.py > gpurun_out/bench_input_pipeline.json 2> gpurun_out/bench_input_pipeline.err
+  echo "bench input pipeline exit $?"; cut -c1-600 gpurun_out/bench_input_pipeline.json
 fi
 if [[ $what == *launches* ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_vpt.csv \
       python bench.py --mode vpt --steps 1 --warmup 1 --no-cpu-baseline --no-roofline --no-e2e > gpurun_out/launches_vpt.log 2>&1
-  echo "launch list exit $?"
+  echo "launch list vpt exit $?"
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches_coop.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-roofline --no-e2e > gpurun_out/launches_coop.log 2>&1
+  echo "launch list coop exit $?"
 fi
 if [[ $what == *ncu* ]]; then
   B="python bench.py --mode vpt --steps 1 --warmup 1 --no-cpu-baseline --no-roofline --no-e2e"
