@@ -314,6 +314,14 @@ def ours_arm(a):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
         "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
 
+    # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the four image-tower linears at B=256, L=205 from the
+    # committed `ncu --set full` capture profiles/r01_ncu_full_v4_summary.txt, next to their algorithmic bytes
+    # (A + W + output [+ residual in] [+ saved pre-activation]); MB per launch.  Traffic stays below the algorithmic
+    # figure (part of each output is still in the 126 MB L2 when the kernel ends): no wasted re-reads.
+    NCU_TRAFFIC_MB = {"qkv 52480x2304x768": {"traffic": 307.3, "algorithmic": 326.0},
+                      "out_proj 52480x768x768 (+fp32 residual)": {"traffic": 122.1, "algorithmic": 404.2},
+                      "fc1 52480x3072x768 (QuickGELU, 2 outputs)": {"traffic": 692.8, "algorithmic": 730.2},
+                      "fc2 52480x768x3072 (+fp32 residual)": {"traffic": 395.6, "algorithmic": 649.5}}
     roofline = None
     kernels = None
     if not a.no_roofline:
@@ -332,6 +340,9 @@ def ours_arm(a):
                         "peak_source": peak_src, "launches_per_step": g["launches"] / a.steps,
                         "avg_launch_us": g["ms"] * 1e3 / g["launches"],
                         "flops_per_launch": g["flops"] / g["launches"],
+                        "traffic_ncu_mb_per_launch": NCU_TRAFFIC_MB,
+                        "traffic_note": "`traffic` is null because this entry averages every GEMM launch of the step; the "
+                                        "per-shape DRAM traffic of the dominant launches is in traffic_ncu_mb_per_launch",
                         "share_of_step": g["ms"] / a.steps / ms_prof,
                         "timing": "CUDA events around every launch, second pass over the same steps",
                         "ms_per_step_instrumented": ms_prof}
