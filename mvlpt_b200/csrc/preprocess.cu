@@ -146,13 +146,11 @@ vpass_kernel(const mvlpt_image_desc* __restrict__ descs, int out_h, int out_w, i
              const int* __restrict__ kk, const unsigned char* __restrict__ tmp, size_t tmp_stride, Norm nm,
              OutT* __restrict__ out) {
     constexpr int P = VEC4 ? 4 : 1;
-    // ToTensor + Normalize of every possible pixel value, once per block (two IEEE divisions each, as torch computes them)
-    __shared__ float lut[3][256];
-    for (int j = threadIdx.x; j < 3 * 256; j += blockDim.x) {
-        const int c = j >> 8;
-        lut[c][j & 255] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)(j & 255), 255.f), nm.mean[c]), nm.std[c]);
-    }
-    __syncthreads();
+    // ToTensor + Normalize: two IEEE divisions, as torch computes them (a 768-entry shared-memory table of all possible
+    // results measured the same: 0.235 vs 0.231 ms per 256 photos)
+    auto norm = [&](int c, int px) -> float {
+        return __fdiv_rn(__fsub_rn(__fdiv_rn((float)px, 255.f), nm.mean[c]), nm.std[c]);
+    };
     const int b = blockIdx.y;
     const int wq = out_w / P;
     const int idx = blockIdx.x * blockDim.x + threadIdx.x;
@@ -185,14 +183,14 @@ vpass_kernel(const mvlpt_image_desc* __restrict__ descs, int out_h, int out_w, i
             OutT w[4];
             __align__(16) OutT v[4];
 #pragma unroll
-            for (int j = 0; j < 4; ++j) w[j] = cvt_out<OutT>(lut[c][clip8(acc[j * 3 + c])]);
+            for (int j = 0; j < 4; ++j) w[j] = cvt_out<OutT>(norm(c, clip8(acc[j * 3 + c])));
 #pragma unroll
             for (int j = 0; j < 4; ++j) v[j] = flip ? w[3 - j] : w[j];  // static indices: selects, no local memory
             OutT* dst = o + (flip ? out_w - 4 - i0 : i0);
             if (sizeof(OutT) == 2) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<const uint2*>(v);
             else *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(v);
         } else {
-            o[flip ? out_w - 1 - i0 : i0] = cvt_out<OutT>(lut[c][clip8(acc[c])]);
+            o[flip ? out_w - 1 - i0 : i0] = cvt_out<OutT>(norm(c, clip8(acc[c])));
         }
     }
 }
