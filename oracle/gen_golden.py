@@ -108,6 +108,9 @@ CASES = [
     dict(name="b16_upt_transformer", arch="ViT-B/16", coop_n_ctx=16, vpt_n_ctx=8, vpt_deep=True, position="middle",
          cut=True, project_method="transformer", project_dim=128, B=2, C=10),
     dict(name="b32_coop_cfg1", arch="ViT-B/32", coop_n_ctx=4, B=1, C=20),
+    dict(name="b16_cocoop", arch="ViT-B/16", cocoop_n_ctx=4, B=2, C=4),
+    dict(name="b16_vpt_deep_project", arch="ViT-B/16", vpt_n_ctx=8, vpt_deep=True, vpt_project=256, B=2, C=6),
+    dict(name="l14_vpt_deep", arch="ViT-L/14", vpt_n_ctx=8, vpt_deep=True, B=1, C=4),
     dict(name="l14_coop_end", arch="ViT-L/14", coop_n_ctx=16, B=1, C=4),
 ]
 
@@ -220,7 +223,7 @@ def main():
     install_stubs()
     out_dir = REPO / "tests" / "golden"
     out_dir.mkdir(parents=True, exist_ok=True)
-    only = sys.argv[1:]
+    only = set(sys.argv[1:])  # python oracle/gen_golden.py [case names]: regenerate only those
     for case in CASES:
         if only and case["name"] not in only:
             continue

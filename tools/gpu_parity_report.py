@@ -6,7 +6,9 @@ from tests.helpers import build_custom_clip, rel_err
 
 names = sys.argv[1:] or ["tiny_coop_end", "tiny_coop_middle_cut", "tiny_coop_front_csc", "tiny_vpt_shallow", "tiny_vpt_deep",
                          "tiny_vpt_deep_taskmask_soft", "tiny_upt_identity", "b16_coop_end", "b16_vpt_deep", "b32_coop_cfg1",
-                         "l14_coop_end", "tiny_cocoop", "tiny_cocoop_vpt_deep"]
+                         "l14_coop_end", "tiny_cocoop", "tiny_cocoop_vpt_deep", "tiny_upt_transformer", "b16_upt_transformer",
+                         "tiny_vpt_deep_project", "tiny_vpt_shallow_project_coop", "b16_cocoop", "b16_vpt_deep_project",
+                         "l14_vpt_deep"]
 bad = 0
 for prec in ("fp32", "fp16"):
     for name in names:
