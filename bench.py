@@ -59,6 +59,9 @@ def parse_args():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--eval", action="store_true",
+                    help="time the inference path (MVLPT.test's inner loop: parse_batch_test -> model_inference -> argmax; "
+                         "SURVEY.md 8f-2) instead of the training step; not a BASELINE metric")
     return ap.parse_args()
 
 
@@ -68,7 +71,8 @@ def workload_name(a) -> str:
            "cocoop": f"MVLPT-CoCoOp n_ctx={COCOOP_N_CTX.get(a.mode, 0)}"}
     ref = {"coop": "BASELINE.json configs[1] shape", "vpt": "BASELINE.json configs[2] shape",
            "upt": "BASELINE.json configs[3] shape", "cocoop": "SURVEY.md 8f-3, not a BASELINE config"}[a.mode]
-    return f"{tag[a.mode]} {ARCH} 224x224 batch={a.batch}/GPU C={a.classes} L_t={a.ctx_len} fp16 ({ref})"
+    ev = " INFERENCE (MVLPT.test inner loop, SURVEY.md 8f-2)" if getattr(a, "eval", False) else ""
+    return f"{tag[a.mode]}{ev} {ARCH} 224x224 batch={a.batch}/GPU C={a.classes} L_t={a.ctx_len} fp16 ({ref})"
 
 
 def make_cfg(a):
@@ -264,6 +268,18 @@ def ours_arm(a):
     dev_batches = [{k: (t.to(dev) if k != "domain" else t) for k, t in hb.items()} for hb in host_batches]
     torch.cuda.synchronize()
 
+    if a.eval:
+        trainer.set_model_mode("eval")
+        trainer.model.hold_text_features(True)  # as MVLPT.test does: the text features are constant during an evaluation
+
+    def step(batch):
+        if not a.eval:
+            return trainer.forward_backward(batch)
+        with torch.no_grad():
+            inp, label, task = trainer.parse_batch_test(batch)
+            pred = trainer.model_inference(inp, task=task).argmax(dim=1)
+        return (pred == label).sum()
+
     def timed(batches, steps):
         dp.barrier()
         torch.cuda.synchronize()
@@ -271,7 +287,9 @@ def ours_arm(a):
         l0 = _lib.launch_count()
         e0.record()
         for i in range(steps):
-            trainer.forward_backward(batches[i % len(batches)])
+            out = step(batches[i % len(batches)])
+        if a.eval:
+            out.item()  # the evaluator's read of the batch result
         e1.record()
         torch.cuda.synchronize()
         dp.barrier()
@@ -280,7 +298,7 @@ def ours_arm(a):
         return float(ms) / steps, (_lib.launch_count() - l0)
 
     for i in range(a.warmup):
-        trainer.forward_backward(dev_batches[i % nbuf])
+        step(dev_batches[i % nbuf])
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
@@ -293,7 +311,7 @@ def ours_arm(a):
     e2e = None
     if not a.no_e2e:
         for i in range(2):
-            trainer.forward_backward(host_batches[i % nbuf])
+            step(host_batches[i % nbuf])
         ms_e2e, _ = timed(host_batches, a.steps)
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(host_batches[0]["img"].numel() * 2 + host_batches[0]["label"].numel() * 8),
@@ -306,6 +324,9 @@ def ours_arm(a):
     # actually executed are reported next to the reference's algorithmic count and are the ones "achieved" uses
     Lk = int(trainer.model.prompt_learner.kernel_len)
     flops_exec = flops_step(synth.ARCHS[ARCH], B, a.classes, Lk, v, n or cc, text_passes=passes)
+    if a.eval:
+        from mvlpt_b200.accounting import flops_inference
+        flops = flops_exec = flops_inference(synth.ARCHS[ARCH], B, a.classes, v)
     peaks = {}
     pk = REPO / "MEASURED_PEAKS.json"
     if pk.exists():
@@ -348,13 +369,14 @@ def ours_arm(a):
                         "ms_per_step_instrumented": ms_prof}
 
     cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline:
+    if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.eval:
         ips, sec, cores, sample, Bc = run_cpu(a, sd, toks, name_lens, steps=2, warmup=1, budget_s=30.0)
         cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
 
     if rank == 0:
         line = {
-            "metric": "prompt-tuning images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
+            "metric": "inference images/sec (MVLPT.test inner loop)" if a.eval else "prompt-tuning images/sec",
+            "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
             "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": workload_name(a), "global_batch": world * B, "parallelism": f"dp{world}",

@@ -26,3 +26,12 @@ def flops_step(arch: dict, B: int, C: int, L_t: int, v: int, n_ctx: int, text_pa
     if n_ctx > 0:
         f += text_passes * C * tower_bwd_flops(L_t, dt, lt) + 2 * B * C * e
     return float(f)
+
+
+def flops_inference(arch: dict, B: int, C: int, v: int) -> float:
+    """One evaluation batch with the text features held (MVLPT.test): image tower forward + logit head."""
+    d, ly, p = arch["vision_width"], arch["vision_layers"], arch["vision_patch_size"]
+    e = arch["embed_dim"]
+    n_p = (arch["image_resolution"] // p) ** 2
+    L = 1 + v + n_p
+    return float(B * (tower_fwd_flops(L, d, ly) + 2 * n_p * d * 3 * p * p + 2 * d * e) + 2 * B * C * e)
