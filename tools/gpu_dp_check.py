@@ -23,12 +23,14 @@ ARCH = "ViT-B/16"
 C, n, v, Bl = 37, 4, 2, 6  # 37 classes: ragged shards
 
 
-def build(dp_group, csc):
+def build(dp_group, csc, cocoop=False):
     cfg = default_cfg()
     T = cfg.TRAINER.MVLPT
     T.PREC = "fp16"
     T.PROJECT_METHOD = "identity"
     T.COOP.N_CTX, T.COOP.CLASS_TOKEN_POSITION, T.COOP.CSC = n, "end", csc
+    if cocoop:  # instance-conditioned branch: no class sharding, B*C text sequences per rank
+        T.COOP.N_CTX, T.COCOOP.N_CTX, T.COCOOP.PREC = 0, n, "fp16"
     T.VPT.N_CTX, T.VPT.DEEP = v, True
     cfg.DATASET.COOP = True
     cfg.MODEL.BACKBONE.NAME = ARCH
@@ -76,6 +78,23 @@ for csc in (False, True):
     if dp.rank == 0:
         print(f"csc={csc}: |sharded - replicated| = {e1:.2e}, |sharded - single rank| = {e2:.2e} (relative to max |g|) "
               f"{'OK' if good else 'BAD'}", flush=True)
+# CoCoOp: per-rank images, all-reduced gradients (context, meta-net weights, visual prompts) vs one rank over the global batch
+tr = build(dp, False, cocoop=True)
+g_dp = step(tr, images[mine], labels[mine], dp.world)
+one = DataParallelGroup.__new__(DataParallelGroup)
+one.enabled, one.world, one.rank, one.group, one.dist = False, 1, 0, None, None
+tr1 = build(one, False, cocoop=True)
+g_one = step(tr1, images, labels, 1)
+views = tr1.model.grad_views()
+off, worst = 0, 0.0
+for k, t in views.items():  # per-tensor scale: the meta-net gradients are orders of magnitude apart
+    a, b = g_dp[off:off + t.numel()], g_one[off:off + t.numel()]
+    worst = max(worst, ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item())
+    off += t.numel()
+good = worst < 2e-2
+ok &= good
+if dp.rank == 0:
+    print(f"cocoop: max over tensors |dp - single rank| / max|g| = {worst:.2e} {'OK' if good else 'BAD'}", flush=True)
 dp.barrier()
 if dp.rank == 0:
     print("ALL OK" if ok else "FAILED", flush=True)
