@@ -280,13 +280,21 @@ def ours_arm(a):
             pred = trainer.model_inference(inp, task=task).argmax(dim=1)
         return (pred == label).sum()
 
-    def timed(batches, steps):
+    def timed(batches, steps, lookahead=False):
+        """`lookahead`: the loop of MVLPT.run_epoch — the host->device copy of batch i+1 is issued (stage_batch) before
+        step i is enqueued; every step's copy still happens inside the timed region."""
         dp.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         l0 = _lib.launch_count()
         e0.record()
+        nxt = trainer.stage_batch(batches[0]) if lookahead else None
         for i in range(steps):
+            if lookahead:
+                cur = nxt
+                nxt = trainer.stage_batch(batches[(i + 1) % len(batches)]) if i + 1 < steps else None
+                out = step(cur)
+                continue
             out = step(batches[i % len(batches)])
         if a.eval:
             out.item()  # the evaluator's read of the batch result
@@ -312,10 +320,11 @@ def ours_arm(a):
     if not a.no_e2e:
         for i in range(2):
             step(host_batches[i % nbuf])
-        ms_e2e, _ = timed(host_batches, a.steps)
+        ms_e2e, _ = timed(host_batches, a.steps, lookahead=True)
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(host_batches[0]["img"].numel() * 2 + host_batches[0]["label"].numel() * 8),
-               "d2h_bytes_per_step": 8}
+               "d2h_bytes_per_step": 8,
+               "loop": "MVLPT.run_epoch's: stage_batch(i+1) (pinned host -> device on the copy stream), then step i"}
 
     cc = COCOOP_N_CTX.get(a.mode, 0)
     passes = B if cc else 1

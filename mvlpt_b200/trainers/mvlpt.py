@@ -935,26 +935,50 @@ class MVLPT:
         label = label.to(self.device, non_blocking=True)
         return input, label, tasks
 
-    def _stage_input(self, input: torch.Tensor) -> torch.Tensor:
-        """Host->device copy of the image batch.  A pinned host batch is copied on a dedicated copy stream into a
-        persistent device buffer and tagged with the event that ends the copy: CustomCLIP runs the (image-independent)
-        text tower first and only then waits for it, so the PCIe transfer hides behind compute.  Anything else takes
-        the reference's plain `.to(device)` route (trainers/mvlpt.py:959-960)."""
+    def _stage_input(self, input: torch.Tensor, label: Optional[torch.Tensor] = None):
+        """Host->device copy of the image batch.  A pinned host batch is copied on a dedicated copy stream into one of two
+        persistent device buffers and tagged with the event that ends the copy: CustomCLIP runs the (image-independent)
+        text tower first and only then waits for it, so the PCIe transfer hides behind compute; with `stage_batch` called
+        one step ahead (run_epoch does) it hides behind the whole previous step.  Anything else takes the reference's plain
+        `.to(device)` route (trainers/mvlpt.py:959-960)."""
         if input.device.type != "cpu" or not input.is_pinned():
             return input.to(self.device, non_blocking=True)
         key = (tuple(input.shape), input.dtype)
         if getattr(self, "_stage_key", None) != key:
             self._stage_key = key
-            self._stage_buf = torch.empty(input.shape, dtype=input.dtype, device=self.device)
+            self._stage_bufs = [torch.empty(input.shape, dtype=input.dtype, device=self.device) for _ in range(2)]
+            self._stage_slot = 0
             self._copy_stream = torch.cuda.Stream(device=self.device)
         cs = self._copy_stream
-        cs.wait_stream(torch.cuda.current_stream(self.device))  # the previous step's readers of the buffer are done
+        buf = self._stage_bufs[self._stage_slot]
+        self._stage_slot ^= 1
+        # everything enqueued so far — in particular the step that last read this buffer — is done before it is overwritten
+        cs.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(cs):
-            self._stage_buf.copy_(input, non_blocking=True)
+            buf.copy_(input, non_blocking=True)
+            if label is not None and label.device.type == "cpu" and label.is_pinned():
+                label = label.to(self.device, non_blocking=True)
+                label.record_stream(torch.cuda.current_stream(self.device))
             ev = torch.cuda.Event()
             ev.record(cs)
-        self._stage_buf._mvlpt_ready = ev
-        return self._stage_buf
+        buf._mvlpt_ready = ev
+        return buf if label is None else (buf, label)
+
+    def stage_batch(self, batch):
+        """Start the host->device copies of a batch AHEAD of its step (pinned host tensors; anything else is returned as
+        is).  Returns a batch of the same structure whose image (and label) live on the device; forward_backward /
+        parse_batch_* accept it like any other batch.  At most one batch may be staged ahead of the one being computed."""
+        if self.cfg.DATASET.COOP:
+            inp_key, lab_key = "img", "label"
+        else:
+            inp_key, lab_key = 0, 1
+        input, label = batch[inp_key], batch[lab_key]
+        if not (isinstance(input, torch.Tensor) and input.device.type == "cpu" and input.is_pinned()):
+            return batch
+        staged = self._stage_input(input, label)
+        out = dict(batch) if isinstance(batch, dict) else list(batch)
+        out[inp_key], out[lab_key] = staged
+        return out if isinstance(batch, dict) else tuple(out)
 
     def parse_batch_train(self, batch):
         return self._parse(batch)
@@ -1096,7 +1120,15 @@ class MVLPT:
         self.set_model_mode("train")
         self.num_batches = len(self.train_loader_x)
         last = None
-        for self.batch_idx, batch in enumerate(self.train_loader_x):
+        it = iter(self.train_loader_x)
+        nxt = next(it, None)
+        nxt = None if nxt is None else self.stage_batch(nxt)
+        self.batch_idx = -1
+        while nxt is not None:
+            batch, self.batch_idx = nxt, self.batch_idx + 1
+            nxt = next(it, None)
+            if nxt is not None:
+                nxt = self.stage_batch(nxt)  # the next batch crosses PCIe while this one is computed
             last = self.forward_backward(batch)
         return last
 

@@ -116,3 +116,35 @@ def test_eval_multitask_elevater_metrics_and_held_text_features():
     assert abs(tr.last_test_results["per_task"]["a"] - want_a) < 1e-9
     assert abs(tr.last_test_results["per_task"]["b"] - want_b) < 1e-9
     assert abs(res - (want_a + want_b) / 2) < 1e-9
+
+
+def test_run_epoch_lookahead_staging_changes_nothing():
+    """run_epoch stages batch i+1 (pinned host -> device on the copy stream, two buffers) before step i is enqueued: the
+    parameters after an epoch are bit-identical to plain forward_backward calls on the same host batches."""
+    from mvlpt_b200 import synth
+    finals = []
+    for mode in ("plain", "epoch"):
+        tr, fx, case, sd, image, pp, upt = _trainer("tiny_vpt_deep", "fp16", lr=0.1)
+        B, C = 4, case["C"]
+        batches = []
+        for i in range(5):
+            g = torch.Generator().manual_seed(40 + i)
+            batches.append({"img": synth.synth_images(B, image.shape[-1], seed=60 + i).half().pin_memory(),
+                            "label": torch.randint(0, C, (B,), generator=g).pin_memory(),
+                            "domain": torch.zeros(B, dtype=torch.long)})
+        if mode == "plain":
+            tr.num_batches = len(batches)
+            for tr.batch_idx, b in enumerate(batches):
+                tr.forward_backward(b)
+        else:
+            tr.train_loader_x = batches
+            out = tr.run_epoch()
+            assert set(out) == {"loss", "acc"} and tr.batch_idx == len(batches) - 1
+        torch.cuda.synchronize()
+        finals.append({k: p.detach().clone() for k, p in tr.model.prompt_learner.named_parameters()})
+    for k in finals[0]:
+        assert torch.equal(finals[0][k], finals[1][k]), k
+    # a staged batch is accepted wherever a batch is
+    staged = tr.stage_batch(batches[0])
+    assert staged["img"].is_cuda and staged["label"].is_cuda and hasattr(staged["img"], "_mvlpt_ready")
+    assert tr.stage_batch({"img": batches[0]["img"].cuda(), "label": batches[0]["label"]})["img"].is_cuda
