@@ -69,13 +69,15 @@ class GpuTransform:
 
     def __init__(self, size: Sequence[int] = (224, 224), mean: Sequence[float] = CLIP_MEAN,
                  std: Sequence[float] = CLIP_STD, mode: str = "train", scale=(0.08, 1.0), ratio=(3.0 / 4.0, 4.0 / 3.0),
-                 flip_p: float = 0.5, normalize: bool = True, resize_edge: Optional[int] = None,
+                 flip_p: Optional[float] = None, normalize: bool = True, resize_edge: Optional[int] = None,
                  out_dtype=torch.float16, device="cuda"):
         if mode not in ("train", "test", "stretch"):
             raise ValueError(f"unknown mode {mode!r}")
         if out_dtype not in (torch.float16, torch.float32):
             raise ValueError("out_dtype must be torch.float16 or torch.float32")
         self.size = (int(size[0]), int(size[1]))
+        if flip_p is None:  # RandomHorizontalFlip belongs to the training stacks only
+            flip_p = 0.5 if mode == "train" else 0.0
         self.mode, self.scale, self.ratio, self.flip_p = mode, tuple(scale), tuple(ratio), float(flip_p)
         self.mean = (ctypes.c_float * 3)(*(mean if normalize else (0.0, 0.0, 0.0)))
         self.std = (ctypes.c_float * 3)(*(std if normalize else (1.0, 1.0, 1.0)))
@@ -96,8 +98,9 @@ class GpuTransform:
             box = random_resized_crop_params(H, W, self.scale, self.ratio)
             flip = int(bool(torch.rand(1) < self.flip_p)) if self.flip_p > 0 else 0
             return box, (sh, sw), (0, 0), flip
-        if self.mode == "stretch":
-            return (0, 0, H, W), (sh, sw), (0, 0), 0
+        if self.mode == "stretch":  # Resize(SIZE) [+ RandomHorizontalFlip when the caller asked for it]
+            flip = int(bool(torch.rand(1) < self.flip_p)) if self.flip_p > 0 else 0
+            return (0, 0, H, W), (sh, sw), (0, 0), flip
         s = self.resize_edge  # Resize(int): shorter edge -> s, the other int(s * long / short); then CenterCrop
         if W <= H:
             rw, rh = s, int(s * H / W)
@@ -179,11 +182,12 @@ def build_transform(cfg, is_train: bool = True, out_dtype=torch.float16, device=
     norm = "normalize" in choices
     if not is_train:
         return GpuTransform(size, mean, std, "test", normalize=norm, out_dtype=out_dtype, device=device)
-    if "random_resized_crop" not in choices:
-        return GpuTransform(size, mean, std, "stretch", normalize=norm, out_dtype=out_dtype, device=device)
+    flip_p = 0.5 if "random_flip" in choices else 0.0
+    if "random_resized_crop" not in choices:  # Dassl then resizes to SIZE first
+        return GpuTransform(size, mean, std, "stretch", flip_p=flip_p, normalize=norm, out_dtype=out_dtype, device=device)
     scale = tuple(getattr(cfg.INPUT, "RRCROP_SCALE", (0.08, 1.0)))
-    return GpuTransform(size, mean, std, "train", scale=scale, flip_p=0.5 if "random_flip" in choices else 0.0,
-                        normalize=norm, out_dtype=out_dtype, device=device)
+    return GpuTransform(size, mean, std, "train", scale=scale, flip_p=flip_p, normalize=norm, out_dtype=out_dtype,
+                        device=device)
 
 
 def elevater_transform(cfg, out_dtype=torch.float16, device="cuda") -> GpuTransform:

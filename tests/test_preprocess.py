@@ -73,3 +73,55 @@ def test_coefficients_are_a_partition_of_unity():
         bounds, kk = P.precompute_coeffs(in_size, out_size)
         assert (bounds[:, 0] >= 0).all() and (bounds[:, 0] + bounds[:, 1] <= in_size).all()
         assert np.abs(kk.sum(1) - (1 << P.PRECISION_BITS)).max() <= kk.shape[1]
+
+
+def test_test_mode_geometry_equals_torchvision_resize_and_center_crop():
+    """Resize(int) output size and CenterCrop offsets for odd aspect ratios, against torchvision on a PIL image."""
+    import torchvision.transforms as T
+    from PIL import Image
+    from mvlpt_b200.input_pipeline import GpuTransform
+    tf = GpuTransform((224, 224), mode="test")
+    for (h, w) in [(375, 500), (500, 375), (224, 224), (225, 223), (1000, 333), (240, 1001), (224, 7000)]:
+        box, (rh, rw), (oy, ox), flip = tf.geometry(h, w)
+        pil = Image.new("RGB", (w, h))
+        r = T.Resize(224, interpolation=T.InterpolationMode.BICUBIC)(pil)
+        assert (r.size[1], r.size[0]) == (rh, rw), (h, w)
+        # CenterCrop offsets: crop a coordinate ramp
+        ramp = np.zeros((rh, rw, 3), np.uint8)
+        ramp[..., 0] = (np.arange(rh) % 256)[:, None]
+        ramp[..., 1] = (np.arange(rw) % 256)[None, :]
+        c = np.asarray(T.CenterCrop((224, 224))(Image.fromarray(ramp)))
+        assert c[0, 0, 0] == oy % 256 and c[0, 0, 1] == ox % 256, (h, w)
+        assert box == (0, 0, h, w) and flip == 0
+
+
+def test_cfg_mapping_follows_the_reference_transform_stacks():
+    """build_transform (Dassl choices of configs/trainers/MVLPT/vit_b16.yaml) and elevater_transform (feature.py:540-553)."""
+    from types import SimpleNamespace as NS
+    from mvlpt_b200.input_pipeline import build_transform, elevater_transform, CLIP_MEAN, CLIP_STD
+    inp = NS(SIZE=(224, 224), INTERPOLATION="bicubic", PIXEL_MEAN=list(CLIP_MEAN), PIXEL_STD=list(CLIP_STD),
+             TRANSFORMS=["random_resized_crop", "random_flip", "normalize"])
+    cfg = NS(INPUT=inp, DATASET=NS(CENTER_CROP=False))
+    t = build_transform(cfg, True)
+    assert (t.mode, t.flip_p, t.scale, t.size) == ("train", 0.5, (0.08, 1.0), (224, 224))
+    assert abs(t.mean[0] - CLIP_MEAN[0]) < 1e-7 and abs(t.std[2] - CLIP_STD[2]) < 1e-7
+    assert build_transform(cfg, False).mode == "test"
+    assert elevater_transform(cfg).mode == "stretch"
+    cfg.DATASET.CENTER_CROP = True
+    e = elevater_transform(cfg)
+    assert e.mode == "test" and e.resize_edge == 224
+    inp.TRANSFORMS = ["normalize"]
+    assert build_transform(cfg, True).mode == "stretch"
+    inp.TRANSFORMS = ["random_flip"]
+    nt = build_transform(cfg, True)
+    assert nt.mode == "stretch" and nt.flip_p == 0.5 and nt.mean[0] == 0.0 and nt.std[0] == 1.0  # ToTensor only
+    torch.manual_seed(0)
+    flips = [nt.geometry(50, 60)[3] for _ in range(200)]
+    assert 60 < sum(flips) < 140
+    assert build_transform(cfg, False).flip_p == 0.0
+    inp.TRANSFORMS = ["colorjitter"]
+    with pytest.raises(NotImplementedError):
+        build_transform(cfg, True)
+    inp.TRANSFORMS, inp.INTERPOLATION = ["normalize"], "bilinear"
+    with pytest.raises(NotImplementedError):
+        build_transform(cfg, True)
