@@ -32,7 +32,10 @@ def default_cfg() -> NS:
                      COOP=NS(N_CTX=0, CSC=False, CTX_INIT="", CLASS_TOKEN_POSITION="middle"),
                      COCOOP=NS(N_CTX=0, CTX_INIT="", PREC="fp16")),
             CUT_CONTEXTLEN=False, ACT_CKPT=1),
-        INPUT=NS(SIZE=(224, 224)),
+        # Dassl's INPUT defaults; every MVLPT YAML overrides INTERPOLATION / PIXEL_* / TRANSFORMS
+        # (configs/trainers/MVLPT/vit_b16.yaml:8-13)
+        INPUT=NS(SIZE=(224, 224), INTERPOLATION="bilinear", TRANSFORMS=(), PIXEL_MEAN=[0.485, 0.456, 0.406],
+                 PIXEL_STD=[0.229, 0.224, 0.225], RRCROP_SCALE=(0.08, 1.0)),
         MODEL=NS(BACKBONE=NS(NAME="ViT-B/16", PATH=""), INIT_WEIGHTS=""),
         OPTIM=NS(NAME="sgd", LR=0.002, MAX_EPOCH=200, LR_SCHEDULER="cosine", WARMUP_EPOCH=1, WARMUP_TYPE="constant",
                  WARMUP_CONS_LR=1e-5, MOMENTUM=0.9, WEIGHT_DECAY=5e-4, SGD_DAMPNING=0, SGD_NESTEROV=False),

@@ -197,3 +197,22 @@ def test_bench_reference_arm_prints_contract_line():
     for k in ("impl", "metric", "value", "unit", "cpu_baseline", "e2e", "config", "higher_is_better"):
         assert k in line
     assert line["impl"] == "reference" and line["cpu_baseline"]["kind"] == "port" and line["value"] > 0
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/configs/trainers/MVLPT"), reason="reference checkout not present")
+def test_reference_yaml_files_load_unchanged_and_select_the_transform_stack():
+    """the reference's own trainer YAMLs drop in through the cfg shim (container-only test)."""
+    import glob
+    from mvlpt_b200.trainers import runtime as R
+    from mvlpt_b200.input_pipeline import build_transform
+    files = sorted(glob.glob("/root/reference/configs/trainers/MVLPT/vit_*.yaml"))
+    assert files
+    for f in files:
+        cfg = R.merge_yaml(R.default_cfg(), f)
+        assert cfg.MODEL.BACKBONE.NAME.startswith("ViT-") and tuple(cfg.INPUT.SIZE) == (224, 224)
+        assert cfg.OPTIM.LR_SCHEDULER == "cosine" and cfg.OPTIM.WARMUP_TYPE == "constant"
+        t = build_transform(cfg, True)
+        assert t.mode == "train" and t.flip_p == 0.5 and abs(t.mean[0] - 0.48145466) < 1e-7
+        assert build_transform(cfg, False).mode == "test"
+    with pytest.raises(NotImplementedError):  # Dassl's own default interpolation is bilinear: not what MVLPT runs with
+        build_transform(R.default_cfg(), True)
