@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "fmha_sm100.cuh"
 #include "fmha_bwd_sm100.cuh"
+#include "fmha_long.cuh"
 
 using namespace nvcuda;
 using namespace mvlpt;
@@ -354,10 +355,12 @@ extern "C" int mvlpt_fmha_fwd(const void* qkv, void* out, void* lse, int N, int 
     if (!qkv || !out || !lse) return fail(MVLPT_EINVAL, "mvlpt_fmha_fwd: null argument");
     if (N <= 0 || L <= 0 || heads <= 0 || d != heads * HD)
         return fail(MVLPT_ESHAPE, "mvlpt_fmha_fwd: need d == heads*64 (got d=%d heads=%d)", d, heads);
-    if (L > 288) return fail(MVLPT_ESHAPE, "mvlpt_fmha_fwd: L=%d > 288 unsupported", L);
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    // longer than the single-pass kernels hold (ViT-L/14@336px: 577 tokens + prompts): streaming kernels
+    if (!fmha_sm100_supported(L) && !(g_force_legacy && L <= 288))
+        return fmha_long_fwd(qkv, out, lse, N, L, d, heads, causal, s);
     const float scale = 0.125f;  // 64^-1/2
     if (fmha_sm100_supported(L) && !g_force_legacy) return fmha_fwd_sm100(qkv, out, lse, N, L, d, heads, causal, s);
     const int Lp = (L + 15) / 16 * 16;
@@ -397,10 +400,10 @@ extern "C" int mvlpt_fmha_bwd(const void* qkv, const void* o, const void* d_o, c
     if (!qkv || !o || !d_o || !lse || !dqkv) return fail(MVLPT_EINVAL, "mvlpt_fmha_bwd: null argument");
     if (N <= 0 || L <= 0 || heads <= 0 || d != heads * HD)
         return fail(MVLPT_ESHAPE, "mvlpt_fmha_bwd: need d == heads*64 (got d=%d heads=%d)", d, heads);
-    if (L > 288) return fail(MVLPT_ESHAPE, "mvlpt_fmha_bwd: L=%d > 288 unsupported", L);
     int rc = require_sm100();
     if (rc) return rc;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (L > 288) return fmha_long_bwd(qkv, o, d_o, lse, dqkv, N, L, d, heads, causal, s);  // see mvlpt_fmha_fwd
     if (fmha_bwd_sm100_supported(L) && !g_force_legacy)
         return fmha_bwd_sm100(qkv, o, d_o, lse, dqkv, N, L, d, heads, causal, s);
     const int Lp = (L + 15) / 16 * 16;

@@ -30,6 +30,9 @@ ARCHS = {
     "ViT-L/14": dict(embed_dim=768, image_resolution=224, vision_layers=24, vision_width=1024, vision_patch_size=14,
                      context_length=77, vocab_size=49408, transformer_width=768, transformer_heads=12,
                      transformer_layers=12),
+    "ViT-L/14@336px": dict(embed_dim=768, image_resolution=336, vision_layers=24, vision_width=1024, vision_patch_size=14,
+                           context_length=77, vocab_size=49408, transformer_width=768, transformer_heads=12,
+                           transformer_layers=12),
     # small shapes for golden fixtures that carry their own activations (heads are still 64 wide)
     "tiny": dict(embed_dim=64, image_resolution=64, vision_layers=3, vision_width=128, vision_patch_size=16,
                  context_length=77, vocab_size=49408, transformer_width=128, transformer_heads=2,

@@ -111,6 +111,8 @@ CASES = [
     dict(name="b16_cocoop", arch="ViT-B/16", cocoop_n_ctx=4, B=2, C=4),
     dict(name="b16_vpt_deep_project", arch="ViT-B/16", vpt_n_ctx=8, vpt_deep=True, vpt_project=256, B=2, C=6),
     dict(name="l14_vpt_deep", arch="ViT-L/14", vpt_n_ctx=8, vpt_deep=True, B=1, C=4),
+    # configs/trainers/MVLPT/vit_l14_336.yaml: 577 image tokens + prompts (the streaming attention kernels)
+    dict(name="l14_336_vpt_deep", arch="ViT-L/14@336px", vpt_n_ctx=4, vpt_deep=True, B=1, C=3),
     dict(name="l14_coop_end", arch="ViT-L/14", coop_n_ctx=16, B=1, C=4),
 ]
 

@@ -45,7 +45,11 @@ def test_gemm(M, N, K, act, resid, f32):
 @pytest.mark.parametrize("N,L,heads,causal", [(3, 197, 12, 0), (2, 205, 12, 0), (2, 50, 12, 0), (1, 257, 16, 0),
                                               (5, 77, 8, 1), (4, 20, 8, 1), (2, 1, 2, 0), (2, 16, 2, 1), (40, 205, 12, 0),
                                               (3, 130, 2, 1), (2, 64, 1, 0), (1, 272, 1, 0), (2, 256, 2, 0), (3, 128, 3, 1),
-                                              (2, 129, 2, 0), (2, 240, 2, 1), (300, 205, 12, 0), (150, 77, 8, 1)])
+                                              (2, 129, 2, 0), (2, 240, 2, 1), (300, 205, 12, 0), (150, 77, 8, 1),
+                                              # longer than the single-pass kernels hold: the streaming kernels
+                                              # (ViT-L/14@336px: 577 tokens + prompts)
+                                              (2, 585, 16, 0), (2, 300, 2, 1), (1, 289, 1, 0), (3, 273, 2, 1), (1, 577, 3, 0),
+                                              (1, 280, 2, 0)])
 def test_fmha_fwd_bwd(N, L, heads, causal):
     from mvlpt_b200 import ops
     torch.manual_seed(1)
