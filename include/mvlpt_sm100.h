@@ -223,7 +223,7 @@ int mvlpt_vpt_proj_bwd(const void* d_out, const void* emb, const void* W, int pa
  *   src: device buffer holding the images as uint8 [H, W, 3] rows packed, image b at byte offset descs[b].src_off;
  *     16-byte aligned and readable up to the next multiple of 16 behind every image (rows are fetched as aligned uint4).
  *   descs: one descriptor per image, given BOTH as a host array (launch planning) and as a device copy (kernels).
- *   out: [B, 3, out_h, out_w] fp32, or fp16 (fp32 result rounded to nearest) when out_f16; out_w <= 256.
+ *   out: [B, 3, out_h, out_w] fp32, or fp16 (fp32 result rounded to nearest) when out_f16.
  *   mean3 / std3: host pointers to 3 floats.  workspace: mvlpt_preprocess_workspace(...) bytes of device memory.
  * ------------------------------------------------------------------------------------------------ */
 typedef struct {

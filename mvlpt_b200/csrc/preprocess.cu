@@ -104,8 +104,7 @@ hpass_kernel(const unsigned char* __restrict__ src, const mvlpt_image_desc* __re
         }
     }
     __syncthreads();
-    const int i = threadIdx.x;
-    if (i >= out_w) return;
+    for (int i = threadIdx.x; i < out_w; i += blockDim.x) {
     const int2 bd = bounds[(size_t)(b * 2) * S + i];
     const int* k = kk + (size_t)(b * 2) * K * S + i;
     int acc[kRowsPerBlock][3];
@@ -129,6 +128,7 @@ hpass_kernel(const unsigned char* __restrict__ src, const mvlpt_image_desc* __re
             o[0] = (unsigned char)clip8(acc[r][0]); o[1] = (unsigned char)clip8(acc[r][1]); o[2] = (unsigned char)clip8(acc[r][2]);
         }
     }
+    }  // output columns
 }
 
 struct Norm {
@@ -208,8 +208,8 @@ int taps(int in_size, int out_size) {  // ksize of Resample.c precompute_coeffs
 
 int make_plan(const mvlpt_image_desc* h, int B, int out_h, int out_w, Plan& p, const char* who) {
     if (!h) return fail(MVLPT_EINVAL, "%s: null descriptors", who);
-    if (B <= 0 || out_h <= 0 || out_w <= 0 || out_w > 256)
-        return fail(MVLPT_EINVAL, "%s: need B > 0 and 0 < out_w <= 256, out_h > 0", who);
+    if (B <= 0 || out_h <= 0 || out_w <= 0 || out_h > 4096 || out_w > 4096)
+        return fail(MVLPT_EINVAL, "%s: need B > 0 and output sizes in [1, 4096]", who);
     p.S = out_h > out_w ? out_h : out_w;
     p.K = 1; p.max_bh = 1; p.max_bw = 1;
     for (int b = 0; b < B; ++b) {

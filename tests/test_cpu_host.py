@@ -209,10 +209,11 @@ def test_reference_yaml_files_load_unchanged_and_select_the_transform_stack():
     assert files
     for f in files:
         cfg = R.merge_yaml(R.default_cfg(), f)
-        assert cfg.MODEL.BACKBONE.NAME.startswith("ViT-") and tuple(cfg.INPUT.SIZE) == (224, 224)
+        side = 336 if cfg.MODEL.BACKBONE.NAME.endswith("@336px") else 224
+        assert cfg.MODEL.BACKBONE.NAME.startswith("ViT-") and tuple(cfg.INPUT.SIZE) == (side, side)
         assert cfg.OPTIM.LR_SCHEDULER == "cosine" and cfg.OPTIM.WARMUP_TYPE == "constant"
         t = build_transform(cfg, True)
-        assert t.mode == "train" and t.flip_p == 0.5 and abs(t.mean[0] - 0.48145466) < 1e-7
+        assert t.mode == "train" and t.flip_p == 0.5 and abs(t.mean[0] - 0.48145466) < 1e-7 and t.size == (side, side)
         assert build_transform(cfg, False).mode == "test"
     with pytest.raises(NotImplementedError):  # Dassl's own default interpolation is bilinear: not what MVLPT runs with
         build_transform(R.default_cfg(), True)
