@@ -31,7 +31,8 @@
 namespace mvlpt {
 
 struct FmhaBwdParams {
-    int L, Lp, heads, d, QT, KC, NQH, causal, num_units;
+    // seq_len < L: every unit packs L / seq_len short sequences under a block-diagonal mask (see FmhaFwd2Params)
+    int L, Lp, heads, d, QT, KC, NQH, causal, num_units, seq_len;
     float scale_log2e;   // hd^-1/2 * log2(e)
     const float* lse;    // [N, heads, L]
     const __half* o;     // [N, L, d]
@@ -276,6 +277,11 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                 const int key = kc * 128 + r;
                 const bool key_ok = key < p.L;
                 const int warp_key_hi = kc * 128 + quarter * 32 + 31;
+                // queries that see this key: [q_first, q_end) — its own sequence, from itself on when causal
+                const int key_seq0 = (key / p.seq_len) * p.seq_len;
+                const int q_first = p.causal ? key : key_seq0;
+                const int q_end = !key_ok ? q_first : (key_seq0 + p.seq_len < p.L ? key_seq0 + p.seq_len : p.L);
+                const bool unpacked = p.seq_len == p.L;
                 for (int qh = 0; qh < NQH; ++qh, ++gi) {
                     const uint32_t b = gi & 1;
                     const int nq = (Lp - qh * 64) < 64 ? (Lp - qh * 64) : 64;
@@ -305,7 +311,7 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                             float pv[16], dsv[16];
                             // warp-uniform: every (key of this warp, query of this group) pair is inside the mask,
                             // except for keys >= L, which are zeroed per thread afterwards
-                            if (q0 + 16 <= p.L && (!p.causal || warp_key_hi <= q0)) {
+                            if (unpacked && q0 + 16 <= p.L && (!p.causal || warp_key_hi <= q0)) {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) {
                                     pv[j] = ex2_approx(fmaf(__uint_as_float(s[j]), sl2, -l2[j]));
@@ -318,7 +324,7 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                             } else {
 #pragma unroll
                                 for (int j = 0; j < 16; ++j) {
-                                    const bool ok = key_ok && q0 + j < p.L && (!p.causal || key <= q0 + j);
+                                    const bool ok = q0 + j >= q_first && q0 + j < q_end;
                                     pv[j] = ok ? ex2_approx(fmaf(__uint_as_float(s[j]), sl2, -l2[j])) : 0.f;
                                     dsv[j] = ok ? pv[j] * (__uint_as_float(dp[j]) - Dq[j]) : 0.f;
                                 }
@@ -383,7 +389,8 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     }
                 }
                 Dv = acc;
-                l2 = p.lse[((size_t)n * p.heads + h) * p.L + q] * 1.4426950408889634f;
+                const int per = p.L / p.seq_len, sq = q / p.seq_len;  // sequences per unit, this row's sequence
+                l2 = p.lse[((size_t)(n * per + sq) * p.heads + h) * p.seq_len + (q - sq * p.seq_len)] * 1.4426950408889634f;
             }
         };
         auto publish_stats = [&](const float (&Dv)[2], const float (&l2)[2]) {
@@ -489,7 +496,24 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 inline bool fmha_bwd_sm100_supported(int L) { return L >= 1 && L <= 256; }
 
 inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const void* lse, void* dqkv, int N, int L,
-                          int d, int heads, int causal, cudaStream_t stream) {
+                          int d, int heads, int causal, cudaStream_t stream, int seq_len = 0) {
+    // short sequences: G = 128 / L of them per unit (same rule as fmha_fwd_sm100: both passes see the same lse layout)
+    static const bool pack = !(getenv("MVLPT_FMHA_PACK") && getenv("MVLPT_FMHA_PACK")[0] == '0');
+    if (seq_len == 0 && pack && L <= 64 && N >= 2) {
+        const int G = 128 / L, groups = N / G, rem = N - groups * G;
+        if (groups > 0) {
+            const int rc = fmha_bwd_sm100(qkv, o, d_o, lse, dqkv, groups, G * L, d, heads, causal, stream, L);
+            if (rc) return rc;
+        }
+        if (rem > 0) {
+            const size_t row0 = (size_t)groups * G * L;
+            return fmha_bwd_sm100(static_cast<const __half*>(qkv) + row0 * 3 * d, static_cast<const __half*>(o) + row0 * d,
+                                  static_cast<const __half*>(d_o) + row0 * d,
+                                  static_cast<const float*>(lse) + (size_t)groups * G * heads * L,
+                                  static_cast<__half*>(dqkv) + row0 * 3 * d, 1, rem * L, d, heads, causal, stream, L);
+        }
+        return MVLPT_OK;
+    }
     const int Lp = (L + 15) / 16 * 16;
     CUtensorMap tq, tdo, tdq;
     {
@@ -518,6 +542,7 @@ inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const
     p.KC = (Lp + 127) / 128;
     p.NQH = (Lp + 63) / 64;
     p.causal = causal;
+    p.seq_len = seq_len > 0 ? seq_len : L;
     p.num_units = N * heads;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     p.lse = static_cast<const float*>(lse);

@@ -162,6 +162,7 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             const uint32_t ph = (it >> 1) & 1;
             const int q = qt * 128 + r;
             const bool warp_live = (qt * 128 + quarter * 32) < p.L;  // warp-uniform
+            constexpr int lo = 0;  // this kernel never packs sequences
             const int lim = p.causal ? (q + 1 < p.L ? q + 1 : p.L) : p.L;  // valid keys: [0, lim)
             mbar_wait(&s_full[slot], ph);
             tc_fence_after();
@@ -173,13 +174,13 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     uint32_t raw[16];
                     tmem_ld_32x32b_x16(t_row + c0, raw);
                     tmem_ld_wait();
-                    if (c0 + 16 <= lim) {
+                    if (c0 >= lo && c0 + 16 <= lim) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(raw[j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (c0 + j < lim) m = fmaxf(m, __uint_as_float(raw[j]));
+                            if (c0 + j >= lo && c0 + j < lim) m = fmaxf(m, __uint_as_float(raw[j]));
                     }
                 }
                 if (m == -INFINITY) m = 0.f;  // rows >= L (never stored)
@@ -278,7 +279,9 @@ fmha_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
 //   * Q / K / V of the next unit stream into a second shared-memory stage while this unit computes.
 // 576 threads: TMA warp, MMA warp, 2 x 8 softmax/epilogue warps; all 512 TMEM columns, one CTA per SM.
 struct FmhaFwd2Params {
-    int L, Lp, heads, QT, num_units, causal;
+    // L rows per unit.  seq_len < L: the unit PACKS L / seq_len short sequences (block-diagonal mask: a row only sees
+    // the keys of its own sequence); seq_len == L: one sequence per unit.
+    int L, Lp, heads, QT, num_units, causal, seq_len;
     float scale_log2e, scale;
     float* lse;  // [N, heads, L]
     uint32_t stage_bytes, off_k, off_v, off_o, off_ones, off_max, off_bar;
@@ -292,6 +295,7 @@ struct FmhaFwd2Params {
 constexpr int kFmhaFwd2Threads = 576;
 constexpr int kFmhaFwd2Group = 256;  // threads of one softmax group
 
+template <bool PACKED>
 __global__ void __launch_bounds__(kFmhaFwd2Threads, 1)
 fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv,
                     const __grid_constant__ CUtensorMap tmap_out, const FmhaFwd2Params p) {
@@ -440,7 +444,11 @@ fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             const uint32_t ph = (uint32_t)(t >> 1) & 1;
             const int q = qt * 128 + r;
             const bool warp_live = (qt * 128 + quarter * 32) < p.L;  // warp-uniform, same for both halves of a quarter
-            const int lim = p.causal ? (q + 1 < p.L ? q + 1 : p.L) : p.L;  // valid keys: [0, lim)
+            // valid keys of this row: [lo, lim) — its own sequence, up to itself when causal.  Without packing lo is the
+            // constant 0 and, for the image tower, lim is warp-uniform: the compiler keeps the branches below uniform.
+            const int lo = PACKED ? (q / p.seq_len) * p.seq_len : 0;
+            const int hi0 = p.causal ? q + 1 : (PACKED ? lo + p.seq_len : p.L);
+            const int lim = hi0 < p.L ? hi0 : p.L;
             mbar_wait(&s_full[g], ph);
             tc_fence_after();
             float m = -INFINITY;
@@ -450,13 +458,13 @@ fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     uint32_t raw[16];
                     tmem_ld_32x32b_x16(t_row + c0, raw);
                     tmem_ld_wait();
-                    if (c0 + 16 <= lim) {
+                    if (c0 >= lo && c0 + 16 <= lim) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) m = fmaxf(m, __uint_as_float(raw[j]));
                     } else {
 #pragma unroll
                         for (int j = 0; j < 16; ++j)
-                            if (c0 + j < lim) m = fmaxf(m, __uint_as_float(raw[j]));
+                            if (c0 + j >= lo && c0 + j < lim) m = fmaxf(m, __uint_as_float(raw[j]));
                     }
                 }
                 *my_max = m;
@@ -472,7 +480,7 @@ fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     tmem_ld_32x32b_x16(t_row + c0, raw);
                     tmem_ld_wait();
                     uint32_t pk[8];
-                    if (c0 + 16 <= lim) {
+                    if (c0 >= lo && c0 + 16 <= lim) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
                             pk[j] = pack_half2(ex2_approx(fmaf(__uint_as_float(raw[2 * j]), sl2, -m2)),
@@ -480,8 +488,9 @@ fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
                     } else {
 #pragma unroll
                         for (int j = 0; j < 8; ++j) {
-                            const float e0 = (c0 + 2 * j < lim) ? ex2_approx(fmaf(__uint_as_float(raw[2 * j]), sl2, -m2)) : 0.f;
-                            const float e1 = (c0 + 2 * j + 1 < lim) ? ex2_approx(fmaf(__uint_as_float(raw[2 * j + 1]), sl2, -m2)) : 0.f;
+                            const int k0 = c0 + 2 * j, k1 = k0 + 1;
+                            const float e0 = (k0 >= lo && k0 < lim) ? ex2_approx(fmaf(__uint_as_float(raw[2 * j]), sl2, -m2)) : 0.f;
+                            const float e1 = (k1 >= lo && k1 < lim) ? ex2_approx(fmaf(__uint_as_float(raw[2 * j + 1]), sl2, -m2)) : 0.f;
                             pk[j] = pack_half2(e0, e1);
                         }
                     }
@@ -502,7 +511,10 @@ fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
             mbar_arrive(&o_read[g]);
             const float sum = __uint_as_float(sm[0]);
             const float inv_sum = 1.f / sum;
-            if (half == 0 && warp_live && q < p.L) p.lse[((size_t)n * p.heads + h) * p.L + q] = m * p.scale + __logf(sum);
+            if (half == 0 && warp_live && q < p.L) {
+                const int per = PACKED ? p.L / p.seq_len : 1, sq = PACKED ? q / p.seq_len : 0;  // sequences per unit, row's sequence
+                p.lse[((size_t)(n * per + sq) * p.heads + h) * p.seq_len + (q - sq * p.seq_len)] = m * p.scale + __logf(sum);
+            }
             // this group's previous TMA store must have finished reading the staging tile
             if (leader) tma_store_wait_read<0>();
             named_bar_sync(1 + g, kFmhaFwd2Group);
@@ -533,8 +545,9 @@ fmha_fwd_tc2_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_con
     }
 }
 
+// seq_len > 0: every unit packs L / seq_len sequences of seq_len rows (N counts the packed groups)
 inline int fmha_fwd2_sm100(const void* qkv, void* out, void* lse, int N, int L, int d, int heads, int causal,
-                           cudaStream_t stream) {
+                           cudaStream_t stream, int seq_len = 0) {
     const int Lp = (L + 15) / 16 * 16;  // <= 256: K / V arrive in one TMA box each
     CUtensorMap tq, tkv, to;
     {
@@ -561,6 +574,7 @@ inline int fmha_fwd2_sm100(const void* qkv, void* out, void* lse, int N, int L, 
     p.QT = (L + 127) / 128;
     p.num_units = N * heads;
     p.causal = causal;
+    p.seq_len = seq_len > 0 ? seq_len : L;
     p.scale = 0.125f;
     p.scale_log2e = 0.125f * 1.4426950408889634f;
     p.lse = static_cast<float*>(lse);
@@ -587,11 +601,15 @@ inline int fmha_fwd2_sm100(const void* qkv, void* out, void* lse, int N, int L, 
     if (smem > 227 * 1024) return fail(MVLPT_ESHAPE, "fmha_fwd2_sm100: L=%d needs %zu bytes of shared memory", L, smem);
     static size_t attr = 0;
     if (smem > attr) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr = smem;
     }
     const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
-    MVLPT_CUDA_OK(launch_pdl(fmha_fwd_tc2_kernel, dim3(grid), dim3(kFmhaFwd2Threads), smem, stream, 1, tq, tkv, to, p));
+    if (p.seq_len != p.L)
+        MVLPT_CUDA_OK(launch_pdl(fmha_fwd_tc2_kernel<true>, dim3(grid), dim3(kFmhaFwd2Threads), smem, stream, 1, tq, tkv, to, p));
+    else
+        MVLPT_CUDA_OK(launch_pdl(fmha_fwd_tc2_kernel<false>, dim3(grid), dim3(kFmhaFwd2Threads), smem, stream, 1, tq, tkv, to, p));
     return launched("fmha_fwd_tc2");
 }
 
@@ -600,6 +618,23 @@ inline bool fmha_sm100_supported(int L) { return L >= 1 && L <= 272; }
 inline int fmha_fwd_sm100(const void* qkv, void* out, void* lse, int N, int L, int d, int heads, int causal,
                           cudaStream_t stream) {
     const int Lp = (L + 15) / 16 * 16;
+    // short sequences (text prompts cut at the last EOT, CoCoOp's B*C prompts): G = 128 / L of them share one 128-row tile
+    // under a block-diagonal mask.  Whole groups first, then the N % G left-over sequences as one smaller group.
+    static const bool pack = !(getenv("MVLPT_FMHA_PACK") && getenv("MVLPT_FMHA_PACK")[0] == '0');
+    if (pack && L <= 64 && N >= 2 && !getenv("MVLPT_FMHA_FWD_V1")) {
+        const int G = 128 / L, groups = N / G, rem = N - groups * G;
+        if (groups > 0) {
+            const int rc = fmha_fwd2_sm100(qkv, out, lse, groups, G * L, d, heads, causal, stream, L);
+            if (rc) return rc;
+        }
+        if (rem > 0) {
+            const size_t row0 = (size_t)groups * G * L;
+            return fmha_fwd2_sm100(static_cast<const __half*>(qkv) + row0 * 3 * d, static_cast<__half*>(out) + row0 * d,
+                                   static_cast<float*>(lse) + (size_t)groups * G * heads * L, 1, rem * L, d, heads, causal,
+                                   stream, L);
+        }
+        return MVLPT_OK;
+    }
     // two stages of Q/K/V fit shared memory up to 240 keys
     if (Lp <= 240 && !getenv("MVLPT_FMHA_FWD_V1")) return fmha_fwd2_sm100(qkv, out, lse, N, L, d, heads, causal, stream);
     const int nbox = (Lp + 255) / 256;  // K / V arrive in nbox TMA boxes of Lp/nbox rows (a multiple of 8)

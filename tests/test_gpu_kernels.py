@@ -49,7 +49,12 @@ def test_gemm(M, N, K, act, resid, f32):
                                               # longer than the single-pass kernels hold: the streaming kernels
                                               # (ViT-L/14@336px: 577 tokens + prompts)
                                               (2, 585, 16, 0), (2, 300, 2, 1), (1, 289, 1, 0), (3, 273, 2, 1), (1, 577, 3, 0),
-                                              (1, 280, 2, 0)])
+                                              (1, 280, 2, 0),
+                                              # short sequences packed several to a tile (block-diagonal mask), with
+                                              # whole groups + a left-over group, causal and not
+                                              (100, 13, 8, 1), (37, 25, 8, 1), (9, 13, 2, 0), (10, 13, 2, 1), (7, 30, 3, 1),
+                                              (5, 64, 2, 0), (3, 50, 12, 0), (21, 9, 1, 1), (2, 2, 1, 1), (130, 1, 2, 0),
+                                              (64, 16, 2, 1), (33, 20, 8, 1)])
 def test_fmha_fwd_bwd(N, L, heads, causal):
     from mvlpt_b200 import ops
     torch.manual_seed(1)
