@@ -394,7 +394,8 @@ def ours_arm(a):
                        "step_tflop_executed": flops_exec / 1e12,
                        "text_causal_cut": {"L_t": a.ctx_len, "rows_computed": Lk,
                                            "note": "rows behind the last EOT cannot influence the EOT rows of a causal "
-                                                   "tower; features and gradients are bit-identical to all L_t rows"},
+                                                   "tower; features and gradients are bit-identical to all L_t rows "
+                                                   "under the same attention tiling"},
                        "step_tflops_achieved_per_gpu": flops_exec / (ms_dev * 1e-3) / 1e12,
                        "step_frac_of_peak": flops_exec / (ms_dev * 1e-3) / 1e12 / tf_peak},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,

@@ -498,7 +498,8 @@ inline bool fmha_bwd_sm100_supported(int L) { return L >= 1 && L <= 256; }
 inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const void* lse, void* dqkv, int N, int L,
                           int d, int heads, int causal, cudaStream_t stream, int seq_len = 0) {
     // short sequences: G = 128 / L of them per unit (same rule as fmha_fwd_sm100: both passes see the same lse layout)
-    static const bool pack = !(getenv("MVLPT_FMHA_PACK") && getenv("MVLPT_FMHA_PACK")[0] == '0');
+    const char* pack_env = getenv("MVLPT_FMHA_PACK");  // read per call: tests switch it inside one process
+    const bool pack = !(pack_env && pack_env[0] == '0');
     if (seq_len == 0 && pack && L <= 64 && N >= 2) {
         const int G = 128 / L, groups = N / G, rem = N - groups * G;
         if (groups > 0) {

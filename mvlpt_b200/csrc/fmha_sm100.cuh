@@ -620,7 +620,8 @@ inline int fmha_fwd_sm100(const void* qkv, void* out, void* lse, int N, int L, i
     const int Lp = (L + 15) / 16 * 16;
     // short sequences (text prompts cut at the last EOT, CoCoOp's B*C prompts): G = 128 / L of them share one 128-row tile
     // under a block-diagonal mask.  Whole groups first, then the N % G left-over sequences as one smaller group.
-    static const bool pack = !(getenv("MVLPT_FMHA_PACK") && getenv("MVLPT_FMHA_PACK")[0] == '0');
+    const char* pack_env = getenv("MVLPT_FMHA_PACK");  // read per call: tests switch it inside one process
+    const bool pack = !(pack_env && pack_env[0] == '0');
     if (pack && L <= 64 && N >= 2 && !getenv("MVLPT_FMHA_FWD_V1")) {
         const int G = 128 / L, groups = N / G, rem = N - groups * G;
         if (groups > 0) {
