@@ -195,3 +195,41 @@ def elevater_transform(cfg, out_dtype=torch.float16, device="cuda") -> GpuTransf
     size, mean, std = _check_input_cfg(cfg)
     mode = "test" if getattr(cfg.DATASET, "CENTER_CROP", False) else "stretch"
     return GpuTransform(size, mean, std, mode, resize_edge=size[0], out_dtype=out_dtype, device=device)
+
+
+def multilabel_to_vec(indices, n_classes: int) -> np.ndarray:
+    """trainers/vision_benchmark/evaluation/feature.py:359-363: class indices -> multi-hot vector."""
+    vec = np.zeros(n_classes, dtype=np.int64)
+    for x in indices:
+        vec[x] = 1
+    return vec
+
+
+class ElevaterBatches:
+    """The loader the reference builds over `MultiTaskTorchDataset` — `get_dataloader` (feature.py:99-107, 851-857):
+    batch 64, unshuffled, last batch kept — with the image transform moved off the CPU workers.
+
+    `items`: any sequence of `(image, class_indices, idx_str, task_id)`, image = PIL image or uint8 [H,W,3] array, the
+    tuple `MultiTaskTorchDataset.__getitem__` (feature.py:733-748) returns before its transform.  Yields the 4-tuples
+    `MVLPT.parse_batch_train/test` index at 0, 1, 3 (trainers/mvlpt.py:957): `(image [B,3,S,S] on the device,
+    target [B, num_classes] multi-hot, [idx_str], task [B] int64 on the CPU)`."""
+
+    def __init__(self, items: Sequence, transform, num_classes: int, batch_size: int = 64):
+        if batch_size <= 0:
+            raise ValueError("batch_size must be positive")
+        self.items, self.transform, self.num_classes, self.batch_size = items, transform, int(num_classes), int(batch_size)
+
+    def __len__(self) -> int:
+        return (len(self.items) + self.batch_size - 1) // self.batch_size
+
+    def __iter__(self):
+        for b0 in range(0, len(self.items), self.batch_size):
+            chunk = [self.items[i] for i in range(b0, min(b0 + self.batch_size, len(self.items)))]
+            arrays = []
+            for im, *_ in chunk:
+                if hasattr(im, "convert"):  # PIL image
+                    im = np.asarray(im.convert("RGB"))
+                arrays.append(im)
+            target = torch.from_numpy(np.stack([multilabel_to_vec(c[1], self.num_classes) for c in chunk]))
+            yield (self.transform(arrays), target, [c[2] for c in chunk],
+                   torch.tensor([int(c[3]) for c in chunk], dtype=torch.int64))

@@ -125,3 +125,29 @@ def test_cfg_mapping_follows_the_reference_transform_stacks():
     inp.TRANSFORMS, inp.INTERPOLATION = ["normalize"], "bilinear"
     with pytest.raises(NotImplementedError):
         build_transform(cfg, True)
+
+
+def test_elevater_batches_follow_the_reference_loader():
+    """get_dataloader (feature.py:99-107): unshuffled, batch 64, last batch kept; items collate to the 4-tuple the trainer
+    indexes at 0, 1, 3; multi-hot targets (feature.py:359-363, 743-744).  The transform is stubbed (no GPU here)."""
+    from PIL import Image
+    from mvlpt_b200.input_pipeline import ElevaterBatches, multilabel_to_vec
+    assert multilabel_to_vec([1, 3], 5).tolist() == [0, 1, 0, 1, 0]
+    seen = []
+
+    def fake_transform(arrays):
+        seen.append([a.shape for a in arrays])
+        assert all(a.dtype == np.uint8 and a.ndim == 3 and a.shape[2] == 3 for a in arrays)
+        return torch.zeros(len(arrays), 3, 4, 4)
+
+    items = []
+    for i in range(150):
+        img = Image.new("L" if i % 7 == 0 else "RGB", (10 + i % 5, 8 + i % 3)) if i % 2 else np.zeros((8, 9, 3), np.uint8)
+        items.append((img, [i % 11] if i % 5 else [i % 11, (i + 3) % 11], f"id{i}", i % 4))
+    loader = ElevaterBatches(items, fake_transform, num_classes=11)
+    batches = list(loader)
+    assert len(loader) == 3 and [b[0].shape[0] for b in batches] == [64, 64, 22]
+    image, target, idx, task = batches[2]
+    assert target.shape == (22, 11) and target.dtype == torch.int64 and idx[0] == "id128" and task.tolist()[:4] == [0, 1, 2, 3]
+    assert target[2].tolist() == multilabel_to_vec([130 % 11, 133 % 11], 11).tolist()   # item 130: two labels
+    assert seen[0][1] == (9, 11, 3)                                                    # PIL (w=11, h=9) -> [H, W, 3]
