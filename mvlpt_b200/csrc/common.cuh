@@ -29,6 +29,23 @@ inline int fail(int code, const char* fmt, ...) {
         if (_e != cudaSuccess) return fail(MVLPT_ECUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
     } while (0)
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute of a kernel: remember, per kernel (one cache
+// object per launch site) and per device, the largest size already granted.
+struct DynSmemCache {
+    std::atomic<size_t> granted[64];
+};
+template <typename K>
+inline int ensure_dyn_smem(K kernel, size_t bytes, DynSmemCache& c) {
+    int dev = 0;
+    MVLPT_CUDA_OK(cudaGetDevice(&dev));
+    std::atomic<size_t>& g = c.granted[dev & 63];
+    if (bytes > g.load(std::memory_order_relaxed)) {
+        MVLPT_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+        g.store(bytes, std::memory_order_relaxed);
+    }
+    return MVLPT_OK;
+}
+
 // Check the launch that just happened and count it.
 inline int launched(const char* what) {
     cudaError_t e = cudaGetLastError();

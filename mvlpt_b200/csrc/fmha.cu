@@ -366,11 +366,8 @@ extern "C" int mvlpt_fmha_fwd(const void* qkv, void* out, void* lse, int N, int 
     const int Lp = (L + 15) / 16 * 16;
     const int ldS = (Lp + 8 > 72) ? Lp + 8 : 72;
     const size_t smem = (size_t)(64 + 2 * Lp) * LDH * 2 + (size_t)64 * ldS * 4;
-    static size_t attr = 0;
-    if (smem > attr) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_wmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    static DynSmemCache attr;
+    if ((rc = ensure_dyn_smem(fmha_fwd_wmma_kernel, smem, attr))) return rc;
     dim3 grid((L + 63) / 64, heads, N);
     fmha_fwd_wmma_kernel<<<grid, 128, smem, s>>>(static_cast<const __half*>(qkv), static_cast<__half*>(out),
                                                  static_cast<float*>(lse), L, Lp, d, heads, causal, scale);
@@ -382,12 +379,8 @@ static int launch_bwd(const void* qkv, const void* o, const void* d_o, const voi
                       int d, int heads, int causal, cudaStream_t s) {
     const int ld = Lp + 8;
     const size_t smem = (size_t)(2 * Lp + 64) * LDH * 2 + (size_t)2 * 32 * ld * 4 + (size_t)2 * 32 * ld * 2 + 64 * 4;
-    static size_t attr = 0;
-    if (smem > attr) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_bwd_wmma_kernel<MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
-        attr = smem;
-    }
+    static DynSmemCache attr;
+    if (int rc = ensure_dyn_smem(fmha_bwd_wmma_kernel<MAXT>, smem, attr)) return rc;
     dim3 grid(heads, N);
     fmha_bwd_wmma_kernel<MAXT><<<grid, 256, smem, s>>>(
         static_cast<const __half*>(qkv), static_cast<const __half*>(o), static_cast<const __half*>(d_o),

@@ -559,11 +559,8 @@ inline int fmha_bwd_sm100(const void* qkv, const void* o, const void* d_o, const
     p.off_bar = p.off_row + 2048u;
     const size_t smem = (size_t)p.off_bar + 128;
     if (smem > 227 * 1024) return fail(MVLPT_ESHAPE, "fmha_bwd_sm100: L=%d needs %zu bytes of shared memory", L, smem);
-    static size_t attr = 0;
-    if (smem > attr) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_bwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    static DynSmemCache attr;
+    if (int rc = ensure_dyn_smem(fmha_bwd_tc_kernel, smem, attr)) return rc;
     const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
     MVLPT_CUDA_OK(launch_pdl(fmha_bwd_tc_kernel, dim3(grid), dim3(kFmhaBwdThreads), smem, stream, 1, tq, tq, tdo, tdq, p));
     return launched("fmha_bwd_tc");

@@ -599,12 +599,9 @@ inline int fmha_fwd2_sm100(const void* qkv, void* out, void* lse, int N, int L, 
     }
     const size_t smem = (size_t)p.off_bar + 128;
     if (smem > 227 * 1024) return fail(MVLPT_ESHAPE, "fmha_fwd2_sm100: L=%d needs %zu bytes of shared memory", L, smem);
-    static size_t attr = 0;
-    if (smem > attr) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    static DynSmemCache attr_plain, attr_packed;
+    if (int rc = ensure_dyn_smem(fmha_fwd_tc2_kernel<false>, smem, attr_plain)) return rc;
+    if (int rc = ensure_dyn_smem(fmha_fwd_tc2_kernel<true>, smem, attr_packed)) return rc;
     const int grid = p.num_units < sm_count() ? p.num_units : sm_count();
     if (p.seq_len != p.L)
         MVLPT_CUDA_OK(launch_pdl(fmha_fwd_tc2_kernel<true>, dim3(grid), dim3(kFmhaFwd2Threads), smem, stream, 1, tq, tkv, to, p));
@@ -677,11 +674,8 @@ inline int fmha_fwd_sm100(const void* qkv, void* out, void* lse, int N, int L, i
     p.off_o = p.off_v + (uint32_t)Lp * 128u;
     p.off_bar = p.off_o + 16384u;
     const size_t smem = (size_t)p.off_bar + 128 + 1024;
-    static size_t attr = 0;
-    if (smem > attr) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(fmha_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = smem;
-    }
+    static DynSmemCache attr;
+    if (int rc = ensure_dyn_smem(fmha_fwd_tc_kernel, smem, attr)) return rc;
     const int per_sm = (smem * 2 <= 227 * 1024 && p.tmem_cols <= 256) ? 2 : 1;
     const int max_ctas = sm_count() * per_sm;
     const int grid = p.num_tiles < max_ctas ? p.num_tiles : max_ctas;

@@ -71,12 +71,8 @@ static int launch_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, c
         int rc = make_tmap_f16(&tx, aux_out, 2, dims, str, box);
         if (rc) return rc;
     }
-    static int attr = 0;
-    if (smem_bytes > attr) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(gemm_f16_tn_kernel<BN, F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes));
-        attr = smem_bytes;
-    }
+    static DynSmemCache attr;
+    if (int rc = ensure_dyn_smem(gemm_f16_tn_kernel<BN, F32>, (size_t)smem_bytes, attr)) return rc;
     const int tiles = cdiv(d->M, kGemmBM) * cdiv(d->N, BN);
     const int grid = tiles < sm_count() ? tiles : sm_count();
     MVLPT_CUDA_OK(launch_pdl(gemm_f16_tn_kernel<BN, F32>, dim3(grid), dim3(kGemmThreads), smem_bytes, stream, 1, ta, tw, to, tx, ti,
@@ -152,12 +148,8 @@ static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* 
         int rc = make_tmap_f16(&tx, aux_out, 2, dims, str, box);
         if (rc) return rc;
     }
-    static int attr = 0;
-    if (smem_bytes > attr) {
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(gemm_f16_tn_2sm_kernel<F32>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           smem_bytes));
-        attr = smem_bytes;
-    }
+    static DynSmemCache attr;
+    if (int rc = ensure_dyn_smem(gemm_f16_tn_2sm_kernel<F32>, (size_t)smem_bytes, attr)) return rc;
     const int tiles = cdiv(d->M, 2 * kGemmBM) * cdiv(d->N, 256);
     const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
     MVLPT_CUDA_OK(launch_pdl(gemm_f16_tn_2sm_kernel<F32>, dim3(2 * pairs), dim3(kGemm2Threads), smem_bytes, stream, 2, ta, tw, to,

@@ -263,8 +263,8 @@ int mvlpt_preprocess(const void* src, const mvlpt_image_desc* descs_host, const 
     const int row_stride = (int)((((size_t)p.max_bw * 3 + 15) & ~size_t(15)) + 16);  // + the row's own misalignment
     const size_t smem = (size_t)row_stride * kRowsPerBlock;
     if (smem > 200 * 1024) return fail(MVLPT_ESHAPE, "mvlpt_preprocess: crop rows of %d pixels do not fit shared memory", p.max_bw);
-    if (smem > 48 * 1024)
-        MVLPT_CUDA_OK(cudaFuncSetAttribute(hpass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static DynSmemCache attr;
+    if (smem > 48 * 1024 && (rc = ensure_dyn_smem(hpass_kernel, smem, attr))) return rc;
     hpass_kernel<<<dim3(cdiv(p.max_bh, kRowsPerBlock), B), 256, smem, s>>>(
         static_cast<const unsigned char*>(src), descs_dev, out_w, p.S, p.K, bounds, kk, tmp, p.tmp_stride, row_stride);
     if ((rc = launched("preprocess hpass"))) return rc;
