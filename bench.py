@@ -1,20 +1,31 @@
 #!/usr/bin/env python
 """Benchmark of the MVLPT prompt-tuning hot path (BASELINE.json: "prompt-tuning images/sec ViT-B/16").
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode coop|vpt|upt]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 1..5] [--scaling weak|strong]
   torchrun ... bench.py --gpus N ...            (one rank per GPU, NCCL; the driver launches it this way for N > 1)
 
 A step = one full prompt-tuning train step (forward, cross-entropy, dgrad-only backward, prompt-gradient all-reduce,
-SGD) of the reference's MVLPT trainer on one synthetic batch.  Default workload = BASELINE.json configs[1]:
-MVLPT-CoOp, ViT-B/16, n_ctx=16, 224x224, 256 images per GPU (weak scaling), 100 classes, L_t=77, fp16.
+SGD) of the reference's MVLPT trainer on one synthetic batch.  `--config` selects one of BASELINE.json's configurations
+(default 2 = configs[1], the one the metric is quoted on at one GPU):
+
+  1  CoOp ViT-B/32 n_ctx=4, Caltech-101 shape (C=100), batch 1                       (configs[0]; the CPU anchor)
+  2  MVLPT-CoOp ViT-B/16 n_ctx=16, 224x224, batch 256, C=100, L_t=77, 'end'          (configs[1])
+  3  MVLPT-VPT-deep ViT-B/16 vctx=8 x 12 layers, 11-task label space C=2193 (the reference's class lists, tokenised by
+     its BPE: tests/golden/b16_vpt_deep_11task.pt), one task id per sample, per-task logit mask, L_t=77    (configs[2])
+  4  MVLPT-UPT ViT-B/16 n_ctx=16 + vctx=8, transformer projection, ImageNet-1k names (tests/golden/
+     b16_coop_c1000_cut.pt), 'middle', the scripts' context cut L_t=30 (`--ctx-len 77` for the uncut variant) (configs[3])
+  5  MVLPT-CoOp ViT-L/14 n_ctx=16, C=1000, L_t=77, batch 512 over 8 GPUs = 64 per GPU                       (configs[4])
+
+`--scaling weak` (default) keeps `--batch` images per GPU; `--scaling strong` splits `--batch` over the ranks.
 
 Prints ONE JSON line on rank 0 (see the contract in the task statement): `value` = images/s with the batch already
 resident in HBM (CUDA events, max over ranks); `e2e` = the same through MVLPT.forward_backward with pinned HOST batches
-(H2D copy + D2H loss read inside the timed region); `roofline` = the tcgen05 GEMM kernel's achieved TFLOP/s from
-per-launch CUDA events in a second pass over the same steps; `cpu_baseline` = the CPU oracle (oracle/mvlpt_oracle.py,
-a restatement of the reference's PyTorch path) on a bounded sample on this host's cores.
+(H2D copy + D2H loss read inside the timed region); `roofline` = the dominant tcgen05 GEMM shape's achieved TFLOP/s from
+per-launch CUDA events in a second pass over the same steps, with its DRAM traffic from the committed ncu capture;
+`cpu_baseline` = the reference's own modules (oracle/_ref, built by oracle/build_ref.py) on a bounded sample on this
+host's cores; `config.eager_fp16_b200_images_per_s` = the same reference modules in fp16 PyTorch-eager on this GPU.
 
-`--impl reference` times that CPU path alone (rank 0 only), same metric/config, and says so in the line.
+`--impl reference` times the reference alone (rank 0 only), same metric/config, and says so in the line.
 """
 from __future__ import annotations
 
@@ -35,15 +46,28 @@ import torch  # noqa: E402
 
 from mvlpt_b200 import synth  # noqa: E402
 
-ARCH = "ViT-B/16"
 MODES = {
-    # name: (coop_n_ctx, vpt_n_ctx, deep, project_method, position)
-    "coop": (16, 0, False, "identity", "end"),
-    "vpt": (0, 8, True, "identity", "end"),
-    "upt": (16, 8, True, "transformer", "end"),
-    "cocoop": (0, 0, False, "identity", "end"),  # COCOOP.N_CTX = 4 (instance-conditioned context)
+    # name: (coop_n_ctx, vpt_n_ctx, deep, project_method)
+    "coop": (16, 0, False, "identity"),
+    "vpt": (0, 8, True, "identity"),
+    "upt": (16, 8, True, "transformer"),
+    "cocoop": (0, 0, False, "identity"),  # COCOOP.N_CTX = 4 (instance-conditioned context)
 }
 COCOOP_N_CTX = {"cocoop": 4}
+
+CONFIGS = {
+    1: dict(mode="coop", arch="ViT-B/32", batch=1, classes=100, ctx_len=77, n_ctx=4, position="end", labels="synthetic",
+            ref="BASELINE.json configs[0]"),
+    2: dict(mode="coop", arch="ViT-B/16", batch=256, classes=100, ctx_len=77, position="end", labels="synthetic",
+            ref="BASELINE.json configs[1]"),
+    3: dict(mode="vpt", arch="ViT-B/16", batch=256, classes=2193, ctx_len=77, position="end", labels="11task",
+            ref="BASELINE.json configs[2]"),
+    4: dict(mode="upt", arch="ViT-B/16", batch=256, classes=1000, ctx_len=30, position="middle", labels="imagenet",
+            ref="BASELINE.json configs[3]"),
+    5: dict(mode="coop", arch="ViT-L/14", batch=64, classes=1000, ctx_len=77, position="end", labels="imagenet",
+            ref="BASELINE.json configs[4] (512 images over 8 GPUs)"),
+}
+LABEL_FIXTURE = {"imagenet": "b16_coop_c1000_cut", "11task": "b16_vpt_deep_11task"}
 
 
 def parse_args():
@@ -52,53 +76,128 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="coop", choices=sorted(MODES))
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU")
-    ap.add_argument("--classes", type=int, default=100)
-    ap.add_argument("--ctx-len", type=int, default=77)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--mode", default=None, choices=sorted(MODES))
+    ap.add_argument("--arch", default=None, choices=[k for k in synth.ARCHS if k != "tiny"])
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (weak) / in total (strong)")
+    ap.add_argument("--classes", type=int, default=None)
+    ap.add_argument("--ctx-len", type=int, default=None)
+    ap.add_argument("--position", default=None, choices=["end", "middle", "front"])
+    ap.add_argument("--labels", default=None, choices=["synthetic", "imagenet", "11task"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--eval", action="store_true",
                     help="time the inference path (MVLPT.test's inner loop: parse_batch_test -> model_inference -> argmax; "
                          "SURVEY.md 8f-2) instead of the training step; not a BASELINE metric")
-    return ap.parse_args()
+    a = ap.parse_args()
+    c = CONFIGS[a.config]
+    explicit = {k: getattr(a, k) is not None for k in ("mode", "arch", "batch", "classes", "ctx_len", "position", "labels")}
+    for k in ("mode", "arch", "batch", "classes", "ctx_len", "position", "labels"):
+        if getattr(a, k) is None:
+            setattr(a, k, c[k])
+    if explicit["classes"] and not explicit["labels"] and a.classes != c["classes"]:
+        a.labels = "synthetic"
+    a.n_ctx_override = c.get("n_ctx") if not explicit["mode"] else None
+    a.config_ref = c["ref"] if not any(explicit.values()) else f"{c['ref']} with overrides " + \
+        ",".join(k for k, v in explicit.items() if v)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    a.global_batch = a.batch * world if a.scaling == "weak" else a.batch
+    if a.global_batch % world:
+        raise SystemExit(f"--scaling strong: batch {a.batch} does not divide over {world} ranks")
+    a.local_batch = a.global_batch // world
+    return a
+
+
+def mode_of(a):
+    n, v, deep, method = MODES[a.mode]
+    if a.n_ctx_override and n:
+        n = a.n_ctx_override
+    return n, v, deep, method
 
 
 def workload_name(a) -> str:
-    n, v, deep, method, pos = MODES[a.mode]
+    n, v, deep, method = mode_of(a)
     tag = {"coop": f"MVLPT-CoOp n_ctx={n}", "vpt": f"MVLPT-VPT-deep vctx={v}", "upt": f"MVLPT-UPT n_ctx={n}+vctx={v}",
-           "cocoop": f"MVLPT-CoCoOp n_ctx={COCOOP_N_CTX.get(a.mode, 0)}"}
-    ref = {"coop": "BASELINE.json configs[1] shape", "vpt": "BASELINE.json configs[2] shape",
-           "upt": "BASELINE.json configs[3] shape", "cocoop": "SURVEY.md 8f-3, not a BASELINE config"}[a.mode]
+           "cocoop": f"MVLPT-CoCoOp n_ctx={COCOOP_N_CTX.get(a.mode, 0)}"}[a.mode]
     ev = " INFERENCE (MVLPT.test inner loop, SURVEY.md 8f-2)" if getattr(a, "eval", False) else ""
-    return f"{tag[a.mode]}{ev} {ARCH} 224x224 batch={a.batch}/GPU C={a.classes} L_t={a.ctx_len} fp16 ({ref})"
+    res = synth.ARCHS[a.arch]["image_resolution"]
+    lab = {"synthetic": "random class-name tokens", "imagenet": "ImageNet-1k names (reference BPE)",
+           "11task": "11-task label space (reference BPE), task id per sample, per-task logit mask"}[a.labels]
+    return (f"{tag}{ev} {a.arch} {res}x{res} batch={a.local_batch}/GPU C={a.classes} L_t={a.ctx_len} "
+            f"'{a.position}' fp16, {lab} ({a.config_ref})")
 
 
 def make_cfg(a):
     from mvlpt_b200.trainers.runtime import default_cfg
-    n, v, deep, method, pos = MODES[a.mode]
+    n, v, deep, method = mode_of(a)
     cfg = default_cfg()
     T = cfg.TRAINER.MVLPT
     T.PREC = "fp16"
     T.PROJECT_METHOD = method
-    T.COOP.N_CTX, T.COOP.CLASS_TOKEN_POSITION = n, pos
+    T.COOP.N_CTX, T.COOP.CLASS_TOKEN_POSITION = n, a.position
     T.VPT.N_CTX, T.VPT.DEEP = v, deep
     T.COCOOP.N_CTX = COCOOP_N_CTX.get(a.mode, 0)
     cfg.DATASET.COOP = True
-    cfg.MODEL.BACKBONE.NAME = ARCH
+    cfg.DATASET.MULTITASK = a.labels == "11task"
+    cfg.DATASET.MULTITASK_LABEL_PERTASK = a.labels == "11task"
+    cfg.MODEL.BACKBONE.NAME = a.arch
+    res = synth.ARCHS[a.arch]["image_resolution"]
+    cfg.INPUT.SIZE = (res, res)
     return cfg
 
 
 def make_problem(a):
-    """Synthetic CLIP weights, class-name token ids, data-manager stub."""
-    n, v, deep, method, pos = MODES[a.mode]
-    sd = synth.synth_clip_state_dict(ARCH, seed=0)
-    toks, name_lens = synth.synth_token_ids(a.classes, n or COCOOP_N_CTX.get(a.mode, 0), context_length=a.ctx_len, seed=3)
+    """Synthetic CLIP weights, class-name token ids, data-manager stub, per-task class counts (11-task only)."""
+    n, v, deep, method = mode_of(a)
+    n_text = n or COCOOP_N_CTX.get(a.mode, 0)
+    sd = synth.synth_clip_state_dict(a.arch, seed=0)
+    task_sizes = None
+    if a.labels == "synthetic":
+        toks, name_lens = synth.synth_token_ids(a.classes, n_text, context_length=a.ctx_len, seed=3)
+    else:
+        fx = torch.load(REPO / "tests" / "golden" / f"{LABEL_FIXTURE[a.labels]}.pt", map_location="cpu", weights_only=False)
+        toks, name_lens = fx["tokenized_prompts"].long(), list(fx["name_lens"])
+        fx_n = fx["case"].get("coop_n_ctx", 0)
+        if fx_n != n_text:
+            raise SystemExit(f"--labels {a.labels} was tokenised with {fx_n} context placeholders, this mode uses {n_text}")
+        if toks.shape[0] != a.classes:
+            raise SystemExit(f"--labels {a.labels} has {toks.shape[0]} classes, not {a.classes}")
+        used = int((toks != 0).sum(1).max())
+        if a.ctx_len < used:
+            raise SystemExit(f"--ctx-len {a.ctx_len} is shorter than the longest prompt ({used})")
+        if toks.shape[1] >= a.ctx_len:
+            toks = toks[:, :a.ctx_len].contiguous()
+        else:
+            toks = torch.cat([toks, torch.zeros(toks.shape[0], a.ctx_len - toks.shape[1], dtype=torch.long)], 1)
+        task_sizes = fx["case"].get("tasks") if a.labels == "11task" else None
     names = [f"class{c}" for c in range(a.classes)]
     dm = NS(dataset=NS(classnames=names), lab2cname={i: nm for i, nm in enumerate(names)}, num_classes=a.classes,
             num_source_domains=1)
-    return sd, toks, name_lens, dm
+    if task_sizes:
+        tn = [f"task{i}" for i in range(len(task_sizes))]
+        dm._num_classes, dm._task_names = a.classes, tn
+        dm._labelmap = {t: list(range(s)) for t, s in zip(tn, task_sizes)}
+    return NS(sd=sd, toks=toks, name_lens=name_lens, dm=dm, task_sizes=task_sizes)
+
+
+def make_batch(a, prob, B, seed):
+    """One synthetic batch in the reference's CoOp-data format {'img','label','domain'} (trainers/mvlpt.py:953-968); with
+    the 11-task label space 'domain' is the task id and the label is uniform inside that task's class range."""
+    res = synth.ARCHS[a.arch]["image_resolution"]
+    img = synth.synth_images(B, res, seed=seed)
+    g = torch.Generator().manual_seed(7 + seed)
+    if prob.task_sizes:
+        sizes = torch.tensor(prob.task_sizes)
+        starts = torch.cumsum(sizes, 0) - sizes
+        task = torch.randint(0, len(sizes), (B,), generator=g)
+        lab = starts[task] + (torch.rand(B, generator=g) * sizes[task]).long().clamp_max(sizes[task] - 1)
+    else:
+        task = torch.zeros(B, dtype=torch.long)
+        lab = torch.randint(0, a.classes, (B,), generator=g)
+    return img, lab, task
 
 
 # --------------------------------------------------------------------------------------------------- clocks
@@ -155,29 +254,93 @@ class ClockSampler:
                 "samples": len(self.samples)}
 
 
-# --------------------------------------------------------------------------------------------------- CPU arm
-def cpu_step_fn(a, sd, toks, name_lens, B):
-    """One reference train step on the CPU oracle for a B-image sample of the workload (fp32, all host threads)."""
-    from oracle import mvlpt_oracle as O
-    n, v, deep, method, pos = MODES[a.mode]
+# --------------------------------------------------------------------------------------------------- reference arms
+def reference_available() -> bool:
+    from oracle import build_ref
+    return build_ref.available()
+
+
+def reference_step_fn(a, prob, B, device="cpu", fp16=False, seed=1):
+    """One train step of the UNMODIFIED reference (oracle/_ref: clip/model.py + trainers/mvlpt.py byte-compiled by
+    oracle/build_ref.py): its CustomCLIP forward, F.cross_entropy, autograd backward and torch.optim.SGD with Dassl's
+    defaults (lr 0.002, momentum 0.9, weight decay 5e-4; trainers/mvlpt.py:910-951), on a B-image sample of the workload
+    with the SAME synthetic weights, class-token ids and prompt parameters as the CUDA arm."""
+    from oracle import build_ref
+    cm, tm = build_ref.import_reference()
+    n, v, deep, method = mode_of(a)
     cc = COCOOP_N_CTX.get(a.mode, 0)
-    pp = synth.synth_prompt_params(ARCH, n, v, deep, project_dim=128 if method == "transformer" else 0, seed=0,
+    arch = synth.ARCHS[a.arch]
+    clip_model = cm.CLIP(**arch)
+    clip_model.load_state_dict(prob.sd)
+    clip_model.eval()
+    if fp16:
+        cm.convert_weights(clip_model)  # what clip.build_model does (clip/model.py:430), the default PREC="fp16" path
+    res = arch["image_resolution"]
+    prec = "fp16" if fp16 else "fp32"
+    cfg = NS(TRAINER=NS(MVLPT=NS(PREC=prec, PROJECT_METHOD=method, PROJECT_DIM=128,
+                                 VPT=NS(N_CTX=v, CTX_INIT="", DROPOUT=0.0, PROJECT=-1, DEEP=deep),
+                                 COOP=NS(N_CTX=n, CTX_INIT="", CSC=False, CLASS_TOKEN_POSITION=a.position),
+                                 COCOOP=NS(N_CTX=cc, CTX_INIT="", PREC=prec)),
+                        CUT_CONTEXTLEN=a.ctx_len < 77, ACT_CKPT=1),
+             INPUT=NS(SIZE=(res, res)), DATASET=NS(MULTITASK_LABEL_PERTASK=bool(prob.task_sizes)))
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):  # the constructor prints its prompt template
+        model = tm.CustomCLIP(cfg, [f"c{i}" for i in range(a.classes)], clip_model, dm=prob.dm if prob.task_sizes else None)
+    pl = model.prompt_learner
+    # identical inputs: the workload's token ids replace the ones the constructor derived from the placeholder names
+    n_text = n or cc
+    with torch.no_grad():
+        emb = clip_model.token_embedding(prob.toks).type(clip_model.dtype)
+    pl.token_prefix, pl.token_suffix = emb[:, :1, :].clone(), emb[:, 1 + n_text:, :].clone()
+    pl.tokenized_prompts = model.tokenized_prompts = prob.toks
+    pl.name_lens = list(prob.name_lens)
+    pp = synth.synth_prompt_params(a.arch, n, v, deep, project_dim=128 if method == "transformer" else 0, seed=0,
                                    cocoop_n_ctx=cc)
-    res = synth.ARCHS[ARCH]["image_resolution"]
-    image = synth.synth_images(B, res, seed=1)
-    g = torch.Generator().manual_seed(2)
-    label = torch.randint(0, a.classes, (B,), generator=g)
-    emb = sd["token_embedding.weight"][toks]
-    kw = dict(embedding=emb, eot_index=toks.argmax(-1), name_lens=name_lens, n_ctx=n, v=v, position=pos,
+    missing, unexpected = pl.load_state_dict(pp, strict=False)
+    assert not unexpected, unexpected
+    for name, p in model.named_parameters():
+        p.requires_grad_("prompt_learner" in name)
+    model.to(device)
+    optim = torch.optim.SGD([p for p in pl.parameters() if p.requires_grad], lr=0.002, momentum=0.9, weight_decay=5e-4)
+    img, lab, task = make_batch(a, prob, B, seed)
+    img = (img.half() if fp16 else img).to(device)
+    lab = lab.to(device)
+    task = task if prob.task_sizes else None
+    F = torch.nn.functional
+
+    def step():
+        out = model(img, task=task)
+        loss = F.cross_entropy(out, lab)
+        optim.zero_grad()
+        loss.backward()
+        optim.step()
+        return float(loss.item())
+
+    return step
+
+
+def port_step_fn(a, prob, B):
+    """Fallback when oracle/_ref was not built: the oracle restatement (oracle/mvlpt_oracle.py) + its SGD."""
+    from oracle import mvlpt_oracle as O
+    n, v, deep, method = mode_of(a)
+    cc = COCOOP_N_CTX.get(a.mode, 0)
+    pp = synth.synth_prompt_params(a.arch, n, v, deep, project_dim=128 if method == "transformer" else 0, seed=0,
+                                   cocoop_n_ctx=cc)
+    image, label, task = make_batch(a, prob, B, 1)
+    emb = prob.sd["token_embedding.weight"][prob.toks]
+    kw = dict(embedding=emb, eot_index=prob.toks.argmax(-1), name_lens=prob.name_lens, n_ctx=n, v=v, position=a.position,
               upt=method == "transformer", cocoop_n_ctx=cc)
+    if prob.task_sizes:
+        ends = torch.cumsum(torch.tensor(prob.task_sizes), 0)
+        kw.update(task=task, task_ranges=torch.stack([ends - torch.tensor(prob.task_sizes), ends], 1))
     params = [p.clone() for p in pp.values()]
     keys = list(pp)
     bufs = [None] * len(params)
 
     def step():
         nonlocal bufs
-        cur = dict(zip(keys, params))
-        _, loss, grads = O.train_step(image, label, sd, cur, **kw)
+        _, loss, grads = O.train_step(image, label, prob.sd, dict(zip(keys, params)), **kw)
         gl = [grads.get(k, torch.zeros_like(p)) for k, p in zip(keys, params)]
         bufs = O.sgd_step(params, gl, bufs, lr=0.002)
         return float(loss)
@@ -185,21 +348,22 @@ def cpu_step_fn(a, sd, toks, name_lens, B):
     return step
 
 
-def run_cpu(a, sd, toks, name_lens, steps, warmup, budget_s):
-    """Times `steps` CPU steps on a sample batch sized so warmup+steps fit `budget_s`; returns images/s + description."""
+def run_cpu(a, prob, steps, warmup, budget_s):
+    """Times `steps` CPU steps of the reference on a sample batch sized so warmup+steps fit `budget_s`."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    B = 4
-    fn = cpu_step_fn(a, sd, toks, name_lens, B)
+    use_ref = reference_available()
+    make = (lambda B: reference_step_fn(a, prob, B)) if use_ref else (lambda B: port_step_fn(a, prob, B))
+    B = min(4, a.local_batch)
+    fn = make(B)
     t0 = time.perf_counter()
     fn()
     t_probe = time.perf_counter() - t0  # includes first-touch cost: an upper bound
-    # per-step cost model: text tower is per step, image tower per image -> scale only the image part up
     total = steps + warmup
     t = t_probe
-    while B * 2 <= min(a.batch, 64) and t * 2 * total < budget_s:  # pessimistic: cost linear in B
+    while B * 2 <= min(a.local_batch, 64) and t * 2 * total < budget_s:  # pessimistic: cost linear in B
         B, t = B * 2, t * 2
-    fn = cpu_step_fn(a, sd, toks, name_lens, B)
+    fn = make(B)
     for _ in range(warmup):
         fn()
     ts = []
@@ -208,35 +372,81 @@ def run_cpu(a, sd, toks, name_lens, steps, warmup, budget_s):
         fn()
         ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
-    sample = (f"oracle/mvlpt_oracle.py train_step+SGD, fp32, {B} images x {a.classes} classes (L_t={a.ctx_len}) per step, "
-              f"{steps} steps after {warmup} warm-up, torch CPU threads={cores}")
-    return B / sec, sec, cores, sample, B
+    what = ("the reference's own CustomCLIP + F.cross_entropy + torch.optim.SGD (oracle/_ref, unmodified modules)" if use_ref
+            else "oracle/mvlpt_oracle.py train_step + SGD (port; oracle/_ref not built)")
+    sample = (f"{what}, fp32, {B} images x {a.classes} classes (L_t={a.ctx_len}) per step, same weights/tokens/prompts as "
+              f"the CUDA arm, {steps} steps after {warmup} warm-up, torch CPU threads={cores}")
+    return dict(ips=B / sec, sec=sec, cores=cores, sample=sample, B=B, kind="reference" if use_ref else "port")
+
+
+def run_eager_gpu(a, prob, steps=8, warmup=3):
+    """SURVEY.md §8d's secondary, honest baseline: the same unmodified reference modules in fp16 PyTorch-eager on cuda:0,
+    full local batch, device-resident inputs, CUDA-event timed.  None when oracle/_ref is absent or it does not fit."""
+    if not (reference_available() and torch.cuda.is_available()):
+        return None
+    try:
+        fn = reference_step_fn(a, prob, a.local_batch, device="cuda", fp16=True)
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"images_per_s": a.local_batch / (ms * 1e-3), "ms_per_step": ms, "batch": a.local_batch, "steps": steps,
+               "what": "reference clip/model.py + trainers/mvlpt.py (oracle/_ref), convert_weights fp16, PyTorch-eager "
+                       f"{torch.__version__} on cuda:0, autograd backward + torch.optim.SGD, loss.item() per step"}
+    except torch.cuda.OutOfMemoryError as e:
+        out = {"images_per_s": None, "error": f"out of memory at batch {a.local_batch}: {str(e)[:120]}"}
+    finally:
+        fn = None
+        torch.cuda.empty_cache()
+    return out
 
 
 def reference_arm(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sd, toks, name_lens, dm = make_problem(a)
-    ips, sec, cores, sample, B = run_cpu(a, sd, toks, name_lens, a.steps, max(1, min(a.warmup, 2)), budget_s=150.0)
+    prob = make_problem(a)
+    r = run_cpu(a, prob, a.steps, max(1, min(a.warmup, 2)), budget_s=150.0)
+    eager = None if a.no_eager_baseline else run_eager_gpu(a, prob)
     line = {
-        "impl": "reference", "metric": "prompt-tuning images/sec", "value": ips, "unit": "images/s", "n_gpus": a.gpus,
-        "steps": a.steps, "warmup": a.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+        "impl": "reference", "metric": "prompt-tuning images/sec", "value": r["ips"], "unit": "images/s", "n_gpus": a.gpus,
+        "steps": a.steps, "warmup": a.warmup, "ms_per_step": r["sec"] * 1e3, "higher_is_better": True, "scaling": a.scaling,
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(a), "cpu_sample_images_per_step": B},
-        "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "config": {"workload": workload_name(a), "cpu_sample_images_per_step": r["B"],
+                   "same_config": r["B"] == a.local_batch,
+                   "sample_note": f"CPU steps run {r['B']} of the {a.local_batch} images of a step (class count, sequence "
+                                  f"lengths, weights and prompts identical); images/s is the normalised figure",
+                   "eager_fp16_b200_images_per_s": None if not eager else eager.get("images_per_s"),
+                   "eager_fp16_b200": eager},
+        "cpu_baseline": {"value": r["ips"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]},
+        "e2e": {"value": r["ips"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
 
 
 # --------------------------------------------------------------------------------------------------- GPU arm
+def ncu_traffic_table():
+    """{shape key: DRAM bytes per launch} parsed from the committed `ncu --set full` capture summary
+    (profiles/ncu_gemm_traffic.json, written by tools/ncu_traffic.py from the .ncu-rep of the same bench command)."""
+    p = REPO / "profiles" / "ncu_gemm_traffic.json"
+    if not p.exists():
+        return {}, None
+    d = json.loads(p.read_text())
+    return d.get("shapes", {}), d.get("source")
+
+
 def ours_arm(a):
     from mvlpt_b200 import _lib, ops
     from mvlpt_b200.trainers.mvlpt import MVLPT
     from mvlpt_b200.trainers.runtime import DataParallelGroup
-    from mvlpt_b200.accounting import flops_step
+    from mvlpt_b200.accounting import flops_step, text_flops
 
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
@@ -247,24 +457,22 @@ def ours_arm(a):
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {a.gpus}")
     _lib.check(_lib.lib().mvlpt_check_device(local_rank), "mvlpt_check_device")
 
-    sd, toks, name_lens, dm = make_problem(a)
+    prob = make_problem(a)
     cfg = make_cfg(a)
-    trainer = MVLPT(cfg, dm=dm, clip_state_dict=sd, device=dev, tokenized_prompts=toks, name_lens=name_lens, dp=dp)
+    trainer = MVLPT(cfg, dm=prob.dm, clip_state_dict=prob.sd, device=dev, tokenized_prompts=prob.toks,
+                    name_lens=prob.name_lens, dp=dp)
     trainer.num_batches = 1 << 30  # never hits the per-epoch LR update inside the timed loop
-    pp = synth.synth_prompt_params(ARCH, *MODES[a.mode][:3], project_dim=128 if MODES[a.mode][3] == "transformer" else 0,
-                                   cocoop_n_ctx=COCOOP_N_CTX.get(a.mode, 0))
+    n, v, deep, method = mode_of(a)
+    cc = COCOOP_N_CTX.get(a.mode, 0)
+    pp = synth.synth_prompt_params(a.arch, n, v, deep, project_dim=128 if method == "transformer" else 0, cocoop_n_ctx=cc)
     trainer.model.prompt_learner.load_state_dict(pp, strict=False)
 
-    n, v, deep, method, pos = MODES[a.mode]
-    res = synth.ARCHS[ARCH]["image_resolution"]
-    B = a.batch
+    B = a.local_batch
     nbuf = 3  # distinct batches rotated so no step re-reads the previous step's inputs
     host_batches = []
     for i in range(nbuf):
-        img = synth.synth_images(B, res, seed=100 + rank * nbuf + i).half().pin_memory()
-        g = torch.Generator().manual_seed(7 + rank * nbuf + i)
-        lab = torch.randint(0, a.classes, (B,), generator=g).pin_memory()
-        host_batches.append({"img": img, "label": lab, "domain": torch.zeros(B, dtype=torch.long)})
+        img, lab, task = make_batch(a, prob, B, seed=100 + rank * nbuf + i)
+        host_batches.append({"img": img.half().pin_memory(), "label": lab.pin_memory(), "domain": task})
     dev_batches = [{k: (t.to(dev) if k != "domain" else t) for k, t in hb.items()} for hb in host_batches]
     torch.cuda.synchronize()
 
@@ -298,6 +506,7 @@ def ours_arm(a):
             out = step(batches[i % len(batches)])
         if a.eval:
             out.item()  # the evaluator's read of the batch result
+        trainer.finish_pending() if hasattr(trainer, "finish_pending") else None
         e1.record()
         torch.cuda.synchronize()
         dp.barrier()
@@ -326,16 +535,30 @@ def ours_arm(a):
                "d2h_bytes_per_step": 8,
                "loop": "MVLPT.run_epoch's: stage_batch(i+1) (pinned host -> device on the copy stream), then step i"}
 
-    cc = COCOOP_N_CTX.get(a.mode, 0)
+    # ---- FLOP accounting: the reference's algorithmic count, and what this step actually executes ----
+    arch = synth.ARCHS[a.arch]
     passes = B if cc else 1
-    flops = flops_step(synth.ARCHS[ARCH], B, a.classes, a.ctx_len, v, n or cc, text_passes=passes)
-    # rows of the causal text tower behind the last EOT are not computed (they cannot reach any output): the FLOPs
-    # actually executed are reported next to the reference's algorithmic count and are the ones "achieved" uses
     Lk = int(trainer.model.prompt_learner.kernel_len)
-    flops_exec = flops_step(synth.ARCHS[ARCH], B, a.classes, Lk, v, n or cc, text_passes=passes)
+    C_local = a.classes  # per rank the text tower covers classes/world under class sharding; FLOPs are per GPU below
+    txt_sharded = world > 1 and trainer.model.shard_text and (n or cc)
+    C_exec = -(-a.classes // world) if txt_sharded else a.classes
+    flops_alg = flops_step(arch, B, a.classes, a.ctx_len, v, n or cc, text_passes=passes)
+    text_cached = (n == 0 and cc == 0)  # no text-side parameter trains: features computed once, then held
+    flops_exec = flops_step(arch, B, 0 if text_cached else C_exec, Lk, v, n or cc, text_passes=passes, head_classes=a.classes)
+    skipped = {
+        "text_forward_cached_tflop": text_flops(arch, a.classes, a.ctx_len, False) / 1e12 if text_cached else 0.0,
+        "text_causal_cut_tflop": 0.0 if text_cached else
+        (text_flops(arch, C_exec, a.ctx_len, bool(n or cc)) - text_flops(arch, C_exec, Lk, bool(n or cc))) * passes / 1e12,
+        "text_class_sharding_tflop": 0.0 if not txt_sharded else
+        (text_flops(arch, a.classes, a.ctx_len, True) - text_flops(arch, C_exec, a.ctx_len, True)) / 1e12,
+        "note": "result-identical work the reference performs every step and this path does not (SURVEY.md App. D): text "
+                "features of a label space no parameter of which trains are computed once; rows behind the last EOT of a "
+                "causal tower cannot reach an EOT row; under data parallelism each rank encodes its shard of the classes",
+    }
     if a.eval:
         from mvlpt_b200.accounting import flops_inference
-        flops = flops_exec = flops_inference(synth.ARCHS[ARCH], B, a.classes, v)
+        flops_alg = flops_exec = flops_inference(arch, B, a.classes, v)
+        skipped = None
     peaks = {}
     pk = REPO / "MEASURED_PEAKS.json"
     if pk.exists():
@@ -344,14 +567,6 @@ def ours_arm(a):
     peak_src = "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)" if peaks else \
         "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)"
 
-    # DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the four image-tower linears at B=256, L=205 from the
-    # committed `ncu --set full` capture profiles/r01_ncu_full_v4_summary.txt, next to their algorithmic bytes
-    # (A + W + output [+ residual in] [+ saved pre-activation]); MB per launch.  Traffic stays below the algorithmic
-    # figure (part of each output is still in the 126 MB L2 when the kernel ends): no wasted re-reads.
-    NCU_TRAFFIC_MB = {"qkv 52480x2304x768": {"traffic": 307.3, "algorithmic": 326.0},
-                      "out_proj 52480x768x768 (+fp32 residual)": {"traffic": 122.1, "algorithmic": 404.2},
-                      "fc1 52480x3072x768 (QuickGELU, 2 outputs)": {"traffic": 692.8, "algorithmic": 730.2},
-                      "fc2 52480x768x3072 (+fp32 residual)": {"traffic": 395.6, "algorithmic": 649.5}}
     roofline = None
     kernels = None
     if not a.no_roofline:
@@ -359,45 +574,61 @@ def ours_arm(a):
         ms_prof, _ = timed(dev_batches, a.steps)
         summ = ops.PROFILER.summary()
         ops.PROFILER = None
-        g = summ.get("gemm_f16_tn")
         kernels = {k: {"launches_per_step": r["launches"] / a.steps, "ms_per_step": r["ms"] / a.steps,
                        "tflops": (r["flops"] / (r["ms"] * 1e-3) / 1e12) if r["ms"] and r["flops"] else None,
                        "gbs": (r["bytes"] / (r["ms"] * 1e-3) / 1e9) if r["ms"] else None} for k, r in summ.items()}
-        if g:
+        g_all = summ.get("gemm_f16_tn")
+        shapes = {k: r for k, r in summ.items() if k.startswith("gemm[")}
+        if shapes:
+            # the dominant kernel = the GEMM shape with the largest share of the step
+            key, g = max(shapes.items(), key=lambda kv: kv[1]["ms"])
+            traffic_tab, traffic_src = ncu_traffic_table()
+            tr = traffic_tab.get(key)
             ach = g["flops"] / (g["ms"] * 1e-3) / 1e12
-            roofline = {"bound": "tensor", "kernel": "gemm_f16_tn_2sm_kernel / gemm_f16_tn_kernel (tcgen05+TMA linear, all launches of the step)",
-                        "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak, "traffic": None,
+            roofline = {"bound": "tensor", "kernel": f"gemm_f16_tn_2sm_kernel {key} (tcgen05 + TMA linear; the shape with "
+                                                     "the largest share of the step)",
+                        "achieved": ach, "peak": tf_peak, "unit": "TFLOP/s", "frac": ach / tf_peak,
+                        "traffic": None if tr is None else tr["dram_bytes"],
+                        "traffic_source": traffic_src if tr is not None else "no ncu capture of this shape committed",
+                        "algorithmic_bytes": g["bytes"] / g["launches"],
                         "peak_source": peak_src, "launches_per_step": g["launches"] / a.steps,
                         "avg_launch_us": g["ms"] * 1e3 / g["launches"],
                         "flops_per_launch": g["flops"] / g["launches"],
-                        "traffic_ncu_mb_per_launch": NCU_TRAFFIC_MB,
-                        "traffic_note": "`traffic` is null because this entry averages every GEMM launch of the step; the "
-                                        "per-shape DRAM traffic of the dominant launches is in traffic_ncu_mb_per_launch",
                         "share_of_step": g["ms"] / a.steps / ms_prof,
+                        "all_gemm_launches": None if not g_all else {
+                            "achieved": g_all["flops"] / (g_all["ms"] * 1e-3) / 1e12,
+                            "frac": g_all["flops"] / (g_all["ms"] * 1e-3) / 1e12 / tf_peak,
+                            "launches_per_step": g_all["launches"] / a.steps,
+                            "share_of_step": g_all["ms"] / a.steps / ms_prof},
                         "timing": "CUDA events around every launch, second pass over the same steps",
                         "ms_per_step_instrumented": ms_prof}
 
-    cpu = None
-    if rank == 0 and world == 1 and not a.no_cpu_baseline and not a.eval:
-        ips, sec, cores, sample, Bc = run_cpu(a, sd, toks, name_lens, steps=2, warmup=1, budget_s=30.0)
-        cpu = {"value": ips, "unit": "images/s", "cores": cores, "kind": "port", "sample": sample}
+    cpu = eager = None
+    if rank == 0 and world == 1 and not a.eval:
+        if not a.no_eager_baseline:
+            del trainer
+            torch.cuda.empty_cache()
+            eager = run_eager_gpu(a, prob)
+        if not a.no_cpu_baseline:
+            r = run_cpu(a, prob, steps=2, warmup=1, budget_s=30.0)
+            cpu = {"value": r["ips"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
     if rank == 0:
         line = {
             "metric": "inference images/sec (MVLPT.test inner loop)" if a.eval else "prompt-tuning images/sec",
             "value": value, "unit": "images/s", "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "warmup": a.warmup, "ms_per_step": ms_dev, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f16", "data": "synthetic",
             "config": {"workload": workload_name(a), "global_batch": world * B, "parallelism": f"dp{world}",
                        "l2": f"{nbuf} distinct input batches rotated; per-step activation working set >> 126 MB L2",
-                       "step_tflop_algorithmic": flops / 1e12,
+                       "step_tflop_algorithmic": flops_alg / 1e12,
                        "step_tflop_executed": flops_exec / 1e12,
-                       "text_causal_cut": {"L_t": a.ctx_len, "rows_computed": Lk,
-                                           "note": "rows behind the last EOT cannot influence the EOT rows of a causal "
-                                                   "tower; features and gradients are bit-identical to all L_t rows "
-                                                   "under the same attention tiling"},
+                       "skipped": skipped,
+                       "text_rows": {"L_t": a.ctx_len, "rows_computed": Lk},
                        "step_tflops_achieved_per_gpu": flops_exec / (ms_dev * 1e-3) / 1e12,
-                       "step_frac_of_peak": flops_exec / (ms_dev * 1e-3) / 1e12 / tf_peak},
+                       "step_frac_of_peak": flops_exec / (ms_dev * 1e-3) / 1e12 / tf_peak,
+                       "eager_fp16_b200_images_per_s": None if not eager else eager.get("images_per_s"),
+                       "eager_fp16_b200": eager},
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "kernels": kernels,
         }

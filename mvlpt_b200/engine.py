@@ -314,6 +314,17 @@ class LogitHead:
         self.e = e
         self.device = device
         self._bufs: Dict[tuple, dict] = {}
+        self._tbufs: Dict[int, dict] = {}
+
+    def text_buffers(self, C: int) -> dict:
+        """Normalised text features of a C-class label space.  They depend on the classes only, never on the batch: every
+        batch size reads the same tensors (a ragged last batch of an evaluation loader must not see stale ones)."""
+        if C not in self._tbufs:
+            dev, e = self.device, self.e
+            z = lambda *s, dt=F16: torch.zeros(*s, device=dev, dtype=dt)
+            self._tbufs[C] = dict(t16=z(C, e), t32=z(C, e, dt=F32), t_inv=z(C, dt=F32), t16_t=z(e, _round_up(C, 8)),
+                                  dt32=z(C, e, dt=F32), dtfeat16=z(C, e))
+        return self._tbufs[C]
 
     def buffers(self, B: int, C: int) -> dict:
         key = (B, C)
@@ -324,17 +335,17 @@ class LogitHead:
             self._bufs[key] = dict(
                 ldc=ldc, ldb=ldb,
                 i16=z(B, e), i32=z(B, e, dt=F32), i_inv=z(B, dt=F32),
-                t16=z(C, e), t32=z(C, e, dt=F32), t_inv=z(C, dt=F32),
                 logits=z(B, ldc, dt=F32), dz16=z(B, ldc), loss_rows=z(B, dt=F32), pred=z(B, dt=I32),
                 hit=z(B, dt=I32), metrics=z(2, dt=F32),
-                t16_t=z(e, ldc), dz16_t=z(C, ldb), i16_t=z(e, ldb),
-                di32=z(B, e, dt=F32), dt32=z(C, e, dt=F32), difeat16=z(B, e), dtfeat16=z(C, e),
+                dz16_t=z(C, ldb), i16_t=z(e, ldb),
+                di32=z(B, e, dt=F32), difeat16=z(B, e),
+                **self.text_buffers(C),
             )
         return self._bufs[key]
 
-    def normalize_text(self, txt_feat: torch.Tensor, B: int):
+    def normalize_text(self, txt_feat: torch.Tensor):
         C = txt_feat.shape[0]
-        bf = self.buffers(B, C)
+        bf = self.text_buffers(C)
         ops.l2norm_fwd(txt_feat, bf["t16"], bf["t32"], bf["t_inv"], C, self.e)
 
     def logits(self, img_feat: torch.Tensor, C: int) -> torch.Tensor:

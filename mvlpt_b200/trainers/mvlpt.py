@@ -170,12 +170,14 @@ class MultitaskVLPromptLearner(nn.Module):
             if method == "identity":
                 pass
             elif method == "transformer":
-                if T.VPT.PROJECT > -1 and T.VPT.PROJECT != vpt_ctx_dim:
+                if T.VPT.PROJECT > -1:
                     # the reference sizes mvlpt_proj_ctx_vpt_pre for the tower width (trainers/mvlpt.py:243-246) and then
-                    # feeds it PROJECT-wide prompts: a shape error there, an explicit one here
-                    raise NotImplementedError("VPT.PROJECT together with PROJECT_METHOD='transformer' is shape-inconsistent "
-                                              "in the reference (trainers/mvlpt.py:243-246,389) unless PROJECT equals the "
-                                              "vision width; not supported")
+                    # feeds it PROJECT-wide prompts: a shape error there, an explicit one here.  PROJECT == vision width
+                    # would run there (UPT projection, then vpt_proj on its output); that chain has no backward here and
+                    # no shipped config uses it, so it is refused as well instead of returning wrong gradients
+                    raise NotImplementedError("VPT.PROJECT together with PROJECT_METHOD='transformer' is not supported "
+                                              "(shape-inconsistent in the reference, trainers/mvlpt.py:243-246,389, "
+                                              "unless PROJECT equals the vision width)")
                 pd = T.PROJECT_DIM
                 ident = lambda: nn.Identity()
                 self.mvlpt_proj_ctx_vpt_pre, self.mvlpt_proj_ctx_vpt_post = ident(), ident()
@@ -458,7 +460,8 @@ class _CustomCLIPFn(torch.autograd.Function):
         logits = model._forward_core(image, task, train)
         ctx.model, ctx.B, ctx.task, ctx.train = model, image.shape[0], task, train
         ctx.n = len(params)
-        return logits[:, :model.prompt_learner.n_cls].to(model.dtype)
+        # a COPY: the engine's logits buffer is reused by the next call with the same (B, C)
+        return logits[:, :model.prompt_learner.n_cls].to(model.dtype, copy=True)
 
     @staticmethod
     def backward(ctx, dlogits):
@@ -569,8 +572,10 @@ class CustomCLIP(nn.Module):
         if pl.cocoop_ctx is not None:
             return self._forward_cocoop(image, ready, vpt, deep, task, train)
         held = getattr(self, "_txt_hold", False) and not train and getattr(self, "_txt_held_for", None) == C
-        if not held and (ctx is not None or not (self.cache_text_features and self._txt_cache_valid == (B, C))):
-            self._text_features(dev, ctx, B, C)
+        # the decision depends on the label space only (never on this rank's batch size): under the class-sharded text
+        # tower every rank must enter the all-gather of _text_features together
+        if not held and (ctx is not None or not (self.cache_text_features and self._txt_cache_valid == C)):
+            self._text_features(dev, ctx, C)
             if getattr(self, "_txt_hold", False) and not train:
                 self._txt_held_for = C
         if ready is not None:
@@ -682,7 +687,7 @@ class CustomCLIP(nn.Module):
         self._txt_hold = bool(on)
         self._txt_held_for = None
 
-    def _text_features(self, dev, ctx, B: int, C: int):
+    def _text_features(self, dev, ctx, C: int):
         """Text tower forward (class-sharded under data parallelism) + L2 normalisation into the head's buffers, on the
         current stream."""
         pl = self.prompt_learner
@@ -703,8 +708,8 @@ class CustomCLIP(nn.Module):
             for r, (a, b) in enumerate(sh["ranges"]):  # drop the padding rows of each rank's slab
                 if b > a:
                     txt_feat[a:b].copy_(sh["gathered"][r, :b - a])
-        head.normalize_text(txt_feat, B)
-        self._txt_cache_valid = (B, C) if ctx is None else False
+        head.normalize_text(txt_feat)  # into buffers shared by every batch size (keyed by C)
+        self._txt_cache_valid = C if ctx is None else False
 
     def grad_buffer(self) -> torch.Tensor:
         """Flat fp32 gradient buffer over every trainable prompt tensor, in named_parameters() order.  The engine writes

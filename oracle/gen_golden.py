@@ -12,12 +12,17 @@ box can rebuild the same parameters without the reference.
 Each fixture stores: the case config, tokenised prompts + name lengths (from the reference BPE tokenizer),
 reference logits / loss / prompt gradients (fp32 run), and, for the "tiny" architecture, intermediate
 activations (image features, text features, assembled prompts, projected prompts).
+
+It also stores the reference's OWN fp16 run of the same step (`ref16_logits`, `ref16_loss`, `ref16_grads`: the model
+converted with the reference's `convert_weights`, TRAINER.MVLPT.PREC="fp16", fp16 image, exactly the default
+configuration of train.py:131).  Its distance from the fp32 run is the yard-stick of the parity tests: a CUDA path that
+computes with fp16 operands is held to 1e-3 (logits) / 5e-3 (gradients) of the fp32 reference, or, where fp16 operand
+rounding makes that unreachable, to never being further from it than the reference's own fp16 path is.
 """
 from __future__ import annotations
 
 import os
 import sys
-import types
 from pathlib import Path
 from types import SimpleNamespace as NS
 
@@ -31,35 +36,9 @@ from mvlpt_b200 import synth  # noqa: E402
 
 
 def install_stubs():
-    def mod(name, **attrs):
-        m = types.ModuleType(name)
-        m.__dict__.update(attrs)
-        sys.modules[name] = m
-        return m
-
-    mod("ftfy", fix_text=lambda s: s)
-
-    class _Registry:
-        def register(self):
-            return lambda cls: cls
-
-    mod("dassl")
-    mod("dassl.engine", TRAINER_REGISTRY=_Registry(), TrainerX=type("TrainerX", (), {}))
-    mod("dassl.metrics", compute_accuracy=None)
-    mod("dassl.utils", load_pretrained_weights=None, load_checkpoint=None)
-    mod("dassl.optim", build_optimizer=None, build_lr_scheduler=None)
-    mod("dassl.data", DataManager=type("DataManager", (), {}))
-    mod("dassl.data.data_manager", build_data_loader=None)
-    mod("dassl.data.datasets", build_dataset=None)
-    mod("dassl.data.samplers", build_sampler=None)
-    mod("dassl.data.transforms", INTERPOLATION_MODES=None, build_transform=None)
-    pkg = mod("trainers")
-    pkg.__path__ = [str(REF / "trainers")]
-    vb = mod("trainers.vision_benchmark")
-    vb.__path__ = []
-    mod("trainers.vision_benchmark.evaluation", construct_dataloader=None, construct_multitask_dataset=None)
-    mod("trainers.vision_benchmark.datasets", class_map_metric={}, get_metric=None)
-    sys.path.insert(0, str(REF))
+    """In-memory stand-ins for dassl / ftfy / the ELEVATER toolkit (oracle/build_ref.py), reference tree on sys.path."""
+    from oracle.build_ref import install_stubs as _stubs
+    _stubs(REF)
 
 
 def make_cfg(case) -> NS:
@@ -114,7 +93,83 @@ CASES = [
     # configs/trainers/MVLPT/vit_l14_336.yaml: 577 image tokens + prompts (the streaming attention kernels)
     dict(name="l14_336_vpt_deep", arch="ViT-L/14@336px", vpt_n_ctx=4, vpt_deep=True, B=1, C=3),
     dict(name="l14_coop_end", arch="ViT-L/14", coop_n_ctx=16, B=1, C=4),
+    # BASELINE class counts.  configs[3]/[4] label space: the 1000 ImageNet names of scripts/classnames.txt, the scripts'
+    # 'middle' position and context-length cut (scripts/mvlpt/main_mt_coopdata_cut.sh:41-47)
+    dict(name="b16_coop_c1000_cut", arch="ViT-B/16", coop_n_ctx=16, position="middle", cut=True, B=2, C=1000,
+         names_from="imagenet"),
+    # configs[2]: the 11 CoOp-source tasks of scripts/mvlpt/main_mt_coopdata_cut.sh:21 (C = 2193), VPT-deep, one task
+    # per sample, per-task logit mask (trainers/mvlpt.py:527-538,573-581), multi-hot soft labels (:914-916)
+    dict(name="b16_vpt_deep_11task", arch="ViT-B/16", vpt_n_ctx=8, vpt_deep=True, B=4, C=2193, task_mask=True,
+         tasks="11task", soft_labels=True, names_from="11task"),
 ]
+
+# the 11 source tasks (scripts/mvlpt/main_mt_coopdata_cut.sh:21) under their ELEVATER names
+# (trainers/vision_benchmark/datasets/prompts.py:3221-3247)
+TASKS_11 = ["imagenet-1k", "caltech-101", "food-101", "stanford-cars", "oxford-iiit-pets", "oxford-flower-102",
+            "fgvc-aircraft-2013b-variants102", "sun397", "dtd", "eurosat_clip", "ucf101"]
+
+
+def label_space(case):
+    """(class names, per-task sizes | None) of a case."""
+    src = case.get("names_from")
+    if src is None:
+        return NAMES[:case["C"]], case.get("tasks")
+    if src == "imagenet":
+        lines = (REF / "scripts" / "classnames.txt").read_text().splitlines()
+        names = [ln.split(" ", 1)[1] for ln in lines if ln.strip()]
+        assert len(names) == case["C"]
+        return names, None
+    if src == "11task":
+        import importlib.util
+        spec = importlib.util.spec_from_file_location(
+            "_ref_prompts", REF / "trainers" / "vision_benchmark" / "datasets" / "prompts.py")
+        pm = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(pm)
+        names, sizes = [], []
+        for t in TASKS_11:
+            names += list(pm.class_map[t])
+            sizes.append(len(pm.class_map[t]))
+        assert len(names) == case["C"], len(names)
+        return names, sizes
+    raise ValueError(src)
+
+
+
+def run_ref16(case, names, dm, pp, image, label_in, task):
+    """The same step through the reference's default fp16 path (train.py:131 PREC="fp16"): weights converted by the
+    reference's own `convert_weights` (clip/model.py:371-392), prompt parameters created in CLIP's dtype, fp16 image,
+    F.cross_entropy on the fp16 logits, autograd backward.  CPU execution of the same modules."""
+    from clip.model import CLIP, convert_weights
+    import trainers.mvlpt as ref
+    if case.get("vpt_dropout"):
+        return {}  # the Bernoulli draws of a second run differ: no like-for-like fp16 yard-stick
+    torch.manual_seed(1234)
+    clip16 = CLIP(**synth.ARCHS[case["arch"]])
+    clip16.load_state_dict(synth.synth_clip_state_dict(case["arch"], seed=0))
+    clip16.eval()
+    convert_weights(clip16)
+    cfg = make_cfg(case)
+    cfg.TRAINER.MVLPT.PREC = "fp16"
+    cfg.TRAINER.MVLPT.COCOOP.PREC = "fp16"
+    model = ref.CustomCLIP(cfg, names, clip16, dm=dm)
+    pl = model.prompt_learner
+    missing, unexpected = pl.load_state_dict(pp, strict=False)
+    assert not unexpected, unexpected
+    for n, p in model.named_parameters():
+        p.requires_grad_("prompt_learner" in n)
+    try:
+        logits = model(image.half(), task=task)
+        lab = label_in
+        if lab.dim() > 1:
+            lab = lab.float()
+            lab = (lab / lab.sum(dim=-1, keepdim=True)).to(logits.dtype)
+        loss = torch.nn.functional.cross_entropy(logits, lab)
+        loss.backward()
+    except RuntimeError as e:  # an op without a CPU half kernel in this torch build
+        print(f"  ref16 run unavailable for {case['name']}: {e}")
+        return {}
+    grads = {n: p.grad.detach().float().clone() for n, p in pl.named_parameters() if p.grad is not None}
+    return dict(ref16_logits=logits.detach().float().clone(), ref16_loss=loss.detach().float().clone(), ref16_grads=grads)
 
 
 def run_case(case, out_dir: Path):
@@ -129,11 +184,13 @@ def run_case(case, out_dir: Path):
     clip_model.eval().float()
 
     C, B = case["C"], case["B"]
-    names = NAMES[:C]
+    names, sizes = label_space(case)
+    case = dict(case)
+    if sizes is not None:
+        case["tasks"] = list(sizes)
     dm = None
     task_ranges = None
     if case.get("task_mask"):
-        sizes = case["tasks"]
         assert sum(sizes) == C
         tnames = [f"t{i}" for i in range(len(sizes))]
         labelmap = {t: list(range(s)) for t, s in zip(tnames, sizes)}
@@ -213,6 +270,7 @@ def run_case(case, out_dir: Path):
             else:
                 imf = fix["image_features"] / fix["image_features"].norm(dim=-1, keepdim=True)
                 fix["cocoop_prompts"] = pl.forward_cocoop(imf)
+    fix.update(run_ref16(case, names, dm, pp, image, label_in, task))
     # margins for the argmax check
     top2 = logits.detach().topk(2, dim=-1).values
     fix["top2_margin"] = (top2[:, 0] - top2[:, 1]).clone()

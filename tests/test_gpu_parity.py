@@ -19,7 +19,7 @@ TINY = ["tiny_coop_end", "tiny_coop_middle_cut", "tiny_coop_front_csc", "tiny_vp
         "tiny_vpt_deep_taskmask_soft", "tiny_upt_identity", "tiny_upt_transformer", "tiny_cocoop", "tiny_cocoop_vpt_deep",
         "tiny_vpt_deep_project", "tiny_vpt_shallow_project_coop"]
 FULL = ["b16_coop_end", "b16_vpt_deep", "b16_upt_transformer", "b32_coop_cfg1", "l14_coop_end", "b16_cocoop",
-        "b16_vpt_deep_project", "l14_vpt_deep", "l14_336_vpt_deep"]
+        "b16_vpt_deep_project", "l14_vpt_deep", "l14_336_vpt_deep", "b16_coop_c1000_cut", "b16_vpt_deep_11task"]
 
 
 def _run(name, prec):

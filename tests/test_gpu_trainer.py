@@ -148,3 +148,53 @@ def test_run_epoch_lookahead_staging_changes_nothing():
     staged = tr.stage_batch(batches[0])
     assert staged["img"].is_cuda and staged["label"].is_cuda and hasattr(staged["img"], "_mvlpt_ready")
     assert tr.stage_batch({"img": batches[0]["img"].cuda(), "label": batches[0]["label"]})["img"].is_cuda
+
+
+@pytest.mark.parametrize("name", ["tiny_coop_end", "tiny_vpt_deep"])
+def test_eval_ragged_last_batch_reads_fresh_text_features(name):
+    """ELEVATER/Dassl test loaders keep the last (smaller) batch.  The held text features belong to the label space, not
+    to a batch size: the logits test() collects for every batch equal per-batch model() calls after the parameters moved."""
+    from tests.helpers import rel_err
+    from mvlpt_b200 import synth
+    tr, fx, case, sd, image, pp, upt = _trainer(name)
+    C = case["C"]
+    imgs = synth.synth_images(7, image.shape[-1], seed=11)
+    labs = torch.arange(7) % C
+    mk = lambda a, b: {"img": imgs[a:b], "label": labs[a:b], "domain": torch.zeros(b - a, dtype=torch.long)}
+    tr.test_loader = [mk(0, 3), mk(3, 6), mk(6, 7)]  # ragged: 3, 3, 1
+    tr.test()  # first evaluation: buffers for B=3 and B=1 now hold these parameters' features
+    with torch.no_grad():  # move the trainable prompts, as an epoch of training would
+        for p in tr.model.prompt_learner.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    tr.model._txt_cache_valid = False
+    collected = []
+    orig = tr.model_inference
+    tr.model_inference = lambda inp, task=None: collected.append(orig(inp, task=task).float().cpu()) or collected[-1].cuda()
+    tr.test()
+    tr.model_inference = orig
+    assert [c.shape[0] for c in collected] == [3, 3, 1]
+    tr.model.hold_text_features(False)
+    for (a, b), got in zip([(0, 3), (3, 6), (6, 7)], collected):
+        with torch.no_grad():
+            want = tr.model(imgs[a:b].cuda()).float().cpu()
+        assert rel_err(got, want) < 1e-6, (a, b)
+
+
+def test_fp32_eval_outputs_do_not_alias_the_engine_buffer():
+    """PREC=fp32: CustomCLIP.forward must hand out its own tensor — two same-size batches kept by the caller (as test()
+    does) stay different."""
+    from mvlpt_b200 import synth
+    tr, fx, case, sd, image, pp, upt = _trainer("tiny_vpt_deep", "fp32")
+    a = synth.synth_images(3, image.shape[-1], seed=21).cuda()
+    b = synth.synth_images(3, image.shape[-1], seed=22).cuda()
+    oa = tr.model_inference(a)
+    keep = oa.clone()
+    ob = tr.model_inference(b)
+    assert oa.data_ptr() != ob.data_ptr()
+    assert torch.equal(oa, keep) and not torch.equal(oa, ob)
+    labs = torch.tensor([0, 1, 2])
+    tr.test_loader = [{"img": a.cpu(), "label": labs, "domain": torch.zeros(3, dtype=torch.long)},
+                      {"img": b.cpu(), "label": labs, "domain": torch.zeros(3, dtype=torch.long)}]
+    res = tr.test()
+    want = 100.0 * float((torch.cat([oa, ob]).argmax(1).cpu() == torch.cat([labs, labs])).float().mean())
+    assert abs(res - want) < 1e-6
