@@ -61,6 +61,16 @@ typedef struct {
 
 int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* aux_in,
                void* aux_out, const void* resid, void* out, mvlpt_stream_t stream);
+/* The residual-stream linears with the FOLLOWING LayerNorm fused in (clip/model.py:185-188: `x + attn(ln_1(x))` feeds
+ * ln_2, `x + mlp(ln_2(x))` feeds the next block's ln_1; LayerNorm itself clip/model.py:153-159):
+ *   out[M,N] fp32 = A.W^T + bias + resid        and        ln_out[M,N] fp16 = LN(out) * ln_gamma + ln_beta
+ * in ONE kernel: a CTA pair owns whole 256-row blocks, accumulates the row sums in the epilogue that already holds the
+ * fp32 row, and normalises the block out of L2 once its last column tile is stored — no LayerNorm kernel re-reads the
+ * stream from HBM.  Needs out_f32, act 0, N == the row width with N % 256 == 0, N <= 1024, M >= 256
+ * (mvlpt_gemm_ln_supported); ln_gamma/ln_beta fp32 [N]; ln_out row stride N. */
+int mvlpt_gemm_ln_supported(int M, int N);
+int mvlpt_gemm_ln(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* resid, void* out,
+                  const void* ln_gamma, const void* ln_beta, void* ln_out, float ln_eps, mvlpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention core, head width 64 (d == heads*64), L <= 288, packed qkv [N*L, 3d] fp16 (Q | K | V).
@@ -118,6 +128,11 @@ int mvlpt_embed_assemble(const void* pe, const void* cls, const void* pos, const
                          mvlpt_stream_t stream);
 int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
                           uint64_t seed, int slab, mvlpt_stream_t stream);
+/* Same, and h[b,1+j] = LN(x[b,1+j]) * gamma + beta (fp16 [B*L, d]) for the rows just written: the block's ln_1 output,
+ * when the previous block's mvlpt_gemm_ln already produced it for all rows (h NULL = plain mvlpt_set_prompt_rows). */
+int mvlpt_set_prompt_rows_ln(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
+                             uint64_t seed, int slab, void* h, const void* gamma, const void* beta, float eps,
+                             mvlpt_stream_t stream);
 int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int d, float inv_scale, int zero_rows,
                       float drop_p, uint64_t seed, int slab, mvlpt_stream_t stream);
 int mvlpt_dropout_keep(void* keep, int B, int v, int d, float drop_p, uint64_t seed, int slab, mvlpt_stream_t stream);

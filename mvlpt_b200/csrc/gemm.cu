@@ -103,13 +103,14 @@ static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* 
         forced = e ? atoi(e) : 0;
     }
     if (forced >= 2 && forced <= kGemmMaxStages2) stages = forced;
-    int slabs = (kGemmSmemBudget + 1024 - stages * kStage) / kGemmSlab;
+    int slabs = (kGemmSmemBudget + 1024 - (ep.ln_out ? 2048 : 0) - stages * kStage) / kGemmSlab;
     int ring = slabs / per;
     if (ring > kGemmMaxRing) ring = kGemmMaxRing;
     if (ring < 2) return fail(MVLPT_ESHAPE, "mvlpt_gemm: no room for the output ring");
     ep.stages = stages;
     ep.ring = ring;
-    const int smem_bytes = stages * kStage + ring * per * kGemmSlab + 256;
+    // 256 B of barriers + TMEM slot, then 2 KB of per-row LayerNorm statistics (fused-LN epilogue)
+    const int smem_bytes = stages * kStage + ring * per * kGemmSlab + 256 + (ep.ln_out ? 2048 : 0);
     CUtensorMap ta, tw, to, tx, ti;
     {
         uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
@@ -150,15 +151,46 @@ static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* 
     }
     static DynSmemCache attr;
     if (int rc = ensure_dyn_smem(gemm_f16_tn_2sm_kernel<F32>, (size_t)smem_bytes, attr)) return rc;
-    const int tiles = cdiv(d->M, 2 * kGemmBM) * cdiv(d->N, 256);
+    // with the fused LayerNorm a pair owns whole 256-row blocks (all column tiles of a block back to back)
+    const int tiles = ep.ln_out ? cdiv(d->M, 2 * kGemmBM) : cdiv(d->M, 2 * kGemmBM) * cdiv(d->N, 256);
     const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
     MVLPT_CUDA_OK(launch_pdl(gemm_f16_tn_2sm_kernel<F32>, dim3(2 * pairs), dim3(kGemm2Threads), smem_bytes, stream, 2, ta, tw, to,
                              tx, ti, d->M, d->N, d->K, ep));
     return launched("gemm_f16_tn_2sm");
 }
 
+static int gemm_impl(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* aux_in,
+                     void* aux_out, const void* resid, void* out, const void* ln_gamma, const void* ln_beta, void* ln_out,
+                     float ln_eps, mvlpt_stream_t stream);
+
 extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias,
                           const void* aux_in, void* aux_out, const void* resid, void* out, mvlpt_stream_t stream) {
+    return gemm_impl(d, A, W, bias, aux_in, aux_out, resid, out, nullptr, nullptr, nullptr, 0.f, stream);
+}
+
+extern "C" int mvlpt_gemm_ln_supported(int M, int N) {
+    static int off = -1;
+    if (off < 0) off = (getenv("MVLPT_GEMM_1SM") || getenv("MVLPT_NO_FUSED_LN")) ? 1 : 0;
+    return !off && M >= 256 && N >= 256 && (N % 256) == 0 && N <= 1024;
+}
+
+extern "C" int mvlpt_gemm_ln(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* resid,
+                             void* out, const void* ln_gamma, const void* ln_beta, void* ln_out, float ln_eps,
+                             mvlpt_stream_t stream) {
+    if (!d || !ln_gamma || !ln_beta || !ln_out) return fail(MVLPT_EINVAL, "mvlpt_gemm_ln: null argument");
+    if (!d->out_f32 || d->act != ACT_NONE) return fail(MVLPT_ESHAPE, "mvlpt_gemm_ln: fp32 output without activation only");
+    if (!mvlpt_gemm_ln_supported(d->M, d->N))
+        return fail(MVLPT_ESHAPE, "mvlpt_gemm_ln: needs M >= 256 and N a multiple of 256 up to 1024 (got M=%d N=%d)", d->M,
+                    d->N);
+    if ((reinterpret_cast<uintptr_t>(ln_gamma) & 15) || (reinterpret_cast<uintptr_t>(ln_beta) & 15) ||
+        (reinterpret_cast<uintptr_t>(ln_out) & 15))
+        return fail(MVLPT_EINVAL, "mvlpt_gemm_ln: gamma/beta/ln_out must be 16-byte aligned");
+    return gemm_impl(d, A, W, bias, nullptr, nullptr, resid, out, ln_gamma, ln_beta, ln_out, ln_eps, stream);
+}
+
+static int gemm_impl(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* aux_in,
+                     void* aux_out, const void* resid, void* out, const void* ln_gamma, const void* ln_beta, void* ln_out,
+                     float ln_eps, mvlpt_stream_t stream) {
     if (!d || !A || !W || !out) return fail(MVLPT_EINVAL, "mvlpt_gemm: null argument");
     if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(MVLPT_EINVAL, "mvlpt_gemm: M,N,K must be positive");
     if (d->lda < d->K || d->ldw < d->K || d->ld_out < d->N)
@@ -189,6 +221,12 @@ extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W
     ep.act = d->act;
     ep.alpha = d->alpha;
     ep.stages = ep.ring = 0;
+    ep.ln_gamma = static_cast<const float*>(ln_gamma);
+    ep.ln_beta = static_cast<const float*>(ln_beta);
+    ep.ln_out = static_cast<__half*>(ln_out);
+    ep.ln_x = static_cast<const float*>(out);
+    ep.ln_ldx = d->ld_out;
+    ep.ln_eps = ln_eps;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (use_2sm(d))
         return d->out_f32 ? launch_gemm_2sm<true>(d, A, W, in, aux_out, out, ep, s)

@@ -37,6 +37,15 @@ struct GemmEpilogue {
     float alpha;
     int stages;          // depth of the operand ring
     int ring;            // output ring slots (each 1 slab, or 2 when has_aux_out)
+    // Fused LayerNorm of the OUTPUT rows (CTA-pair kernel, fp32 output, N == the row width): the residual-stream GEMMs
+    // (out-proj, FC2) also emit h = LN(out) * gamma + beta as fp16, i.e. the ln_2 / next block's ln_1 of
+    // clip/model.py:186-187, so no separate LayerNorm kernel reads the stream back from HBM.
+    const float* ln_gamma;  // [N] or nullptr (no fusion)
+    const float* ln_beta;   // [N]
+    __half* ln_out;         // [M, N] fp16, row stride N
+    const float* ln_x;      // the fp32 output buffer itself (read back from L2 once its row block is complete)
+    int ln_ldx;             // its row stride in elements
+    float ln_eps;
 };
 
 constexpr int kGemmBM = 128;
@@ -392,6 +401,22 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const int n_tiles = (N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (K + kGemmBK - 1) / kGemmBK;
+    // Tile schedule of this pair.  Default: tiles pair, pair + num_pairs, ... of the row-major (m, n) tile grid.  With the
+    // fused LayerNorm a pair owns whole 256-row blocks — all n_tiles column tiles of a block back to back — so that the
+    // epilogue sees complete rows and can finish their statistics.
+    const bool by_rows = OUT_F32 && ep.ln_out != nullptr;
+    const int my_tiles = by_rows ? (pair < m_tiles ? ((m_tiles - 1 - pair) / num_pairs + 1) * n_tiles : 0)
+                                 : (pair < num_tiles ? (num_tiles - 1 - pair) / num_pairs + 1 : 0);
+    auto tile_of = [&](int it, int& mt, int& nt) {
+        if (by_rows) {
+            mt = pair + (it / n_tiles) * num_pairs;
+            nt = it % n_tiles;
+        } else {
+            const int t = pair + it * num_pairs;
+            mt = t / n_tiles;
+            nt = t % n_tiles;
+        }
+    };
 
     if (warp == 0 && lane == 0) {
         if (smem_u32(smem) & 1023u) {
@@ -430,9 +455,11 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-                const int m0 = (tile / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM;
-                const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
+            for (int it = 0; it < my_tiles; ++it) {
+                int mt, nt;
+                tile_of(it, mt, nt);
+                const int m0 = mt * (2 * kGemmBM) + (int)rank * kGemmBM;
+                const int n0 = nt * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);  // both CTAs' bytes
@@ -453,7 +480,7 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            for (int it = 0; it < my_tiles; ++it) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -494,23 +521,28 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         int acc = 0;
         uint32_t acc_phase = 0;
         int g = 0;  // steps done by this CTA
-        const int my_tiles = pair < num_tiles ? (num_tiles - 1 - pair) / num_pairs + 1 : 0;
         const int total_steps = my_tiles * kSteps;
         // TMA load of the epilogue input of step gg into its ring slot (issuer thread only)
         auto issue_in = [&](int gg) {
             if (gg >= total_steps) return;
-            const int t = pair + (gg / kSteps) * num_pairs;
-            const int mm = (t / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM, nn = (t % n_tiles) * BN + (gg % kSteps) * SW;
+            int mt, nt;
+            tile_of(gg / kSteps, mt, nt);
+            const int mm = mt * (2 * kGemmBM) + (int)rank * kGemmBM, nn = nt * BN + (gg % kSteps) * SW;
             const int slot = gg % R;
             mbar_arrive_expect_tx(&in_full[slot], kGemmSlab);
             tma_load_2d(smem_e + slot * kGemmSlab, &tmap_in, &in_full[slot], nn, mm);
         };
         if (has_in && issuer)
             for (int gg = 0; gg < R - 1; ++gg) issue_in(gg);
+        // fused LayerNorm: running sum / sum of squares of this thread's half of its output row
+        float ln_s1 = 0.f, ln_s2 = 0.f;
+        float2* ln_stats = reinterpret_cast<float2*>(tmem_slot + 4);  // [128 rows][2 column halves], 2 KB behind the barriers
 
-        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-            const int m0 = (tile / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM;
-            const int n0 = (tile % n_tiles) * BN;
+        for (int it = 0; it < my_tiles; ++it) {
+            int mt, nt;
+            tile_of(it, mt, nt);
+            const int m0 = mt * (2 * kGemmBM) + (int)rank * kGemmBM;
+            const int n0 = nt * BN;
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * HC;
@@ -584,6 +616,13 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         *dst = make_uint4(__float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
                                           __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
                     }
+                    if (by_rows) {
+#pragma unroll
+                        for (int j = 0; j < HC; ++j) {
+                            ln_s1 += v[j];
+                            ln_s2 = fmaf(v[j], v[j], ln_s2);
+                        }
+                    }
                 } else {
                     // fp16 slab row = 64 columns = 8 units of 8; this thread fills units 4*half .. 4*half+3
                     if (ep.act == ACT_QUICKGELU) {
@@ -633,6 +672,68 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if constexpr (OUT_F32) {
+                if (by_rows && nt == n_tiles - 1) {
+                    // ---- the 128 rows of this CTA are complete: finish LayerNorm (clip/model.py:153-159) ----
+                    ln_stats[r * 2 + half] = make_float2(ln_s1, ln_s2);
+                    ln_s1 = ln_s2 = 0.f;
+                    if (issuer) {
+                        tma_store_wait_all();  // the row block has reached L2 (completion, not just the smem reads)
+                        asm volatile("fence.proxy.async.global;" ::: "memory");
+                    }
+                    gemm_bar_sync256();
+                    const int ew = warp - 2;       // 8 warps x 16 rows; a warp reads 512 contiguous bytes of one row
+                    const int nchunk = N >> 7;     // 128-column chunks of a row (N % 256 == 0, N <= 1024)
+                    const float inv_n = 1.f / (float)N;
+#pragma unroll 1
+                    for (int i = 0; i < 16; i += 2) {
+                        const int r0 = ew * 16 + i;
+                        const int gm0 = m0 + r0, gm1 = gm0 + 1;
+                        float4 xa[8], xb[8];
+                        const float* pa = ep.ln_x + (size_t)gm0 * ep.ln_ldx + lane * 4;
+                        const float* pb = pa + ep.ln_ldx;
+#pragma unroll
+                        for (int ch = 0; ch < 8; ++ch)
+                            if (ch < nchunk) {
+                                if (gm0 < M) xa[ch] = __ldcg(reinterpret_cast<const float4*>(pa + ch * 128));
+                                if (gm1 < M) xb[ch] = __ldcg(reinterpret_cast<const float4*>(pb + ch * 128));
+                            }
+                        const float2 a0 = ln_stats[r0 * 2], a1 = ln_stats[r0 * 2 + 1];
+                        const float2 b0 = ln_stats[r0 * 2 + 2], b1 = ln_stats[r0 * 2 + 3];
+                        const float mean_a = (a0.x + a1.x) * inv_n, mean_b = (b0.x + b1.x) * inv_n;
+                        const float rstd_a = rsqrtf(fmaxf((a0.y + a1.y) * inv_n - mean_a * mean_a, 0.f) + ep.ln_eps);
+                        const float rstd_b = rsqrtf(fmaxf((b0.y + b1.y) * inv_n - mean_b * mean_b, 0.f) + ep.ln_eps);
+                        __half* ya = ep.ln_out + (size_t)gm0 * N + lane * 4;
+                        __half* yb = ya + N;
+#pragma unroll
+                        for (int ch = 0; ch < 8; ++ch)
+                            if (ch < nchunk) {
+                                // gamma / beta: 2 x 16 bytes per lane and chunk out of L1 (the same 2N floats for every row)
+                                const float4 gm = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + ch * 128 + lane * 4));
+                                const float4 bt = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + ch * 128 + lane * 4));
+                                if (gm0 < M) {
+                                    const float4 x = xa[ch];
+                                    uint2 o;
+                                    o.x = pack_h2(fmaf((x.x - mean_a) * rstd_a, gm.x, bt.x),
+                                                  fmaf((x.y - mean_a) * rstd_a, gm.y, bt.y));
+                                    o.y = pack_h2(fmaf((x.z - mean_a) * rstd_a, gm.z, bt.z),
+                                                  fmaf((x.w - mean_a) * rstd_a, gm.w, bt.w));
+                                    *reinterpret_cast<uint2*>(ya + ch * 128) = o;
+                                }
+                                if (gm1 < M) {
+                                    const float4 x = xb[ch];
+                                    uint2 o;
+                                    o.x = pack_h2(fmaf((x.x - mean_b) * rstd_b, gm.x, bt.x),
+                                                  fmaf((x.y - mean_b) * rstd_b, gm.y, bt.y));
+                                    o.y = pack_h2(fmaf((x.z - mean_b) * rstd_b, gm.z, bt.z),
+                                                  fmaf((x.w - mean_b) * rstd_b, gm.w, bt.w));
+                                    *reinterpret_cast<uint2*>(yb + ch * 128) = o;
+                                }
+                            }
+                    }
+                    gemm_bar_sync256();  // ln_stats is rewritten at the end of the next row block
+                }
+            }
         }
         if (issuer) tma_store_wait_all();
     }

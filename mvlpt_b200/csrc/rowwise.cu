@@ -345,9 +345,12 @@ __device__ __forceinline__ float4 drop_scale4(unsigned long long bits, unsigned 
 }
 
 // x[b, 1+j] = prompt[j]  (deep prompt replacement before block l >= 1), times the dropout keep mask / (1-p) when thr > 0
+// With h != nullptr the LayerNorm of the new rows (the ln_1 of the block about to run) is written to h as well: the
+// fused-LayerNorm GEMM of the previous block normalised the rows this kernel replaces.
 __global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __restrict__ prompt, int prompt_f16, int B,
                                        int L, int v, int d, unsigned thr, float keep_scale, unsigned long long seed,
-                                       int slab) {
+                                       int slab, __half* __restrict__ h, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, float eps) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= B * v) return;
@@ -366,6 +369,12 @@ __global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __rest
         }
     }
     row_store(row, x + ((size_t)b * L + 1 + j) * d, d, lane);
+    if (h) {
+        float mean, rstd;
+        row_stats(row, d, lane, eps, mean, rstd);
+        row_affine(row, gamma, beta, d, lane, mean, rstd);
+        row_store_h(row, h + ((size_t)b * L + 1 + j) * d, d, lane);
+    }
 }
 
 // keep[b, j, c] in {0,1}: the mask the two kernels above/below apply (for tests and for replaying a step elsewhere)
@@ -600,7 +609,15 @@ int drop_params(float p, const char* who, unsigned& thr, float& keep_scale) {
 
 int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
                           uint64_t seed, int slab, mvlpt_stream_t stream) {
+    return mvlpt_set_prompt_rows_ln(x, prompt, prompt_f16, B, L, v, d, drop_p, seed, slab, nullptr, nullptr, nullptr, 0.f,
+                                    stream);
+}
+
+int mvlpt_set_prompt_rows_ln(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
+                             uint64_t seed, int slab, void* h, const void* gamma, const void* beta, float eps,
+                             mvlpt_stream_t stream) {
     if (!x || !prompt) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows: null argument");
+    if (h && (!gamma || !beta)) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows_ln: h needs gamma and beta");
     if (B <= 0 || v <= 0 || L < 1 + v) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows: bad sizes");
     int rc = check_d(d, "mvlpt_set_prompt_rows");
     if (rc) return rc;
@@ -609,7 +626,8 @@ int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, in
     if ((rc = drop_params(drop_p, "mvlpt_set_prompt_rows", thr, ks))) return rc;
     if ((rc = require_sm100())) return rc;
     set_prompt_rows_kernel<<<cdiv(B * v, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<float*>(x), prompt, prompt_f16, B, L, v, d, thr, ks, seed, slab);
+        static_cast<float*>(x), prompt, prompt_f16, B, L, v, d, thr, ks, seed, slab, static_cast<__half*>(h),
+        static_cast<const float*>(gamma), static_cast<const float*>(beta), eps);
     return launched("set_prompt_rows");
 }
 

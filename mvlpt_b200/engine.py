@@ -101,17 +101,31 @@ class TowerBuffers:
         return self.xmid[l] if self.train else self.x[0]
 
 
-def block_forward(w: BlockWeights, a: TowerBuffers, l: int, causal: bool):
-    """x += attn(ln_1(x)); x += mlp(ln_2(x))   — clip/model.py:185-188."""
+def block_forward(w: BlockWeights, a: TowerBuffers, l: int, causal: bool, h_ready: bool = False, next_ln=None) -> bool:
+    """x += attn(ln_1(x)); x += mlp(ln_2(x))   — clip/model.py:185-188.
+
+    Five launches when the shape allows the fused LayerNorm (ops.gemm_ln_supported): QKV, attention, out-proj (+ residual
+    + ln_2), FC1 (+ QuickGELU), FC2 (+ residual + the NEXT block's ln_1 when `next_ln` = (gamma, beta) is given).
+    `h_ready`: a.h already holds ln_1(x) (written by the previous block's FC2).  Returns whether a.h holds `next_ln`
+    of the output on exit."""
     M, d, i = a.M, a.d, a.idx(l)
     xin, xmid, xout = a.x_in(l), a.x_mid(l), a.x_out(l)
-    ops.ln_fwd(xin, w.ln1_g, w.ln1_b, a.h, M, d)
+    fuse = ops.gemm_ln_supported(M, d)
+    if not h_ready:
+        ops.ln_fwd(xin, w.ln1_g, w.ln1_b, a.h, M, d)
     ops.gemm(a.h, w.w_qkv, a.qkv[i], bias=w.b_qkv)
     ops.fmha_fwd(a.qkv[i], a.o[i], a.lse[i], a.N, a.L, d, a.heads, causal)
-    ops.gemm(a.o[i], w.w_o, xmid, bias=w.b_o, resid=xin)
-    ops.ln_fwd(xmid, w.ln2_g, w.ln2_b, a.h, M, d)
+    if fuse:
+        ops.gemm(a.o[i], w.w_o, xmid, bias=w.b_o, resid=xin, ln=(w.ln2_g, w.ln2_b, a.h))
+    else:
+        ops.gemm(a.o[i], w.w_o, xmid, bias=w.b_o, resid=xin)
+        ops.ln_fwd(xmid, w.ln2_g, w.ln2_b, a.h, M, d)
     ops.gemm(a.h, w.w_fc, a.g, bias=w.b_fc, act=ops.ACT_QUICKGELU, aux_out=a.t[i] if a.train else None)
+    if fuse and next_ln is not None:
+        ops.gemm(a.g, w.w_pr, xout, bias=w.b_pr, resid=xmid, ln=(next_ln[0], next_ln[1], a.h))
+        return True
     ops.gemm(a.g, w.w_pr, xout, bias=w.b_pr, resid=xmid)
+    return False
 
 
 def block_backward(w: BlockWeights, a: TowerBuffers, l: int, causal: bool):
@@ -199,14 +213,19 @@ class ImageTower:
         bf["drop"] = (drop_p, drop_seed)
         run = self.executed_layers(None if vpt_deep is None else vpt_deep.shape[0])
         last = a.x_in(0)
-        for l in run:
+        h_ready = False
+        for k, l in enumerate(run):
+            blk = self.blocks[l]
             if vpt_deep is not None and l >= 1:
                 # rows 1..v of the previous output are discarded and replaced (trainers/mvlpt.py:74-82)
                 src = a.x_in(l)
                 if a.train and last is not src:
                     src.copy_(last)  # only reachable through the skipped-layer quirk
-                ops.set_prompt_rows(src, vpt_deep[l - 1], B, a.L, v, self.d, drop_p, drop_seed, l)
-            block_forward(self.blocks[l], a, l, causal=False)
+                ops.set_prompt_rows(src, vpt_deep[l - 1], B, a.L, v, self.d, drop_p, drop_seed, l,
+                                    ln=(blk.ln1_g, blk.ln1_b, a.h) if h_ready else None)
+            nxt = self.blocks[run[k + 1]] if k + 1 < len(run) else None
+            h_ready = block_forward(blk, a, l, causal=False, h_ready=h_ready,
+                                    next_ln=None if nxt is None else (nxt.ln1_g, nxt.ln1_b))
             last = a.x_out(l)
         bf["final"] = last
         bf["run"] = run
@@ -280,8 +299,11 @@ class TextTower:
         bf = self.buffers(N, Lt, train)
         a: TowerBuffers = bf["act"]
         assemble(a.x_in(0))
+        h_ready = False
         for l in range(self.layers):
-            block_forward(self.blocks[l], a, l, causal=True)
+            nxt = self.blocks[l + 1] if l + 1 < self.layers else None
+            h_ready = block_forward(self.blocks[l], a, l, causal=True, h_ready=h_ready,
+                                    next_ln=None if nxt is None else (nxt.ln1_g, nxt.ln1_b))
         bf["final"] = a.x_out(self.layers - 1)
         ops.ln_fwd(bf["final"], self.ln_g, self.ln_b, bf["pooled"], N, d, row_index=eot_rows)
         ops.gemm(bf["pooled"], self.proj_t, bf["feat"])

@@ -65,9 +65,15 @@ def _chk(t: torch.Tensor, dtype, name: str):
                               f"contig={t.is_contiguous()}")
 
 
+def gemm_ln_supported(M: int, N: int) -> bool:
+    """Can the residual-stream linear of this shape carry the following LayerNorm (mvlpt_gemm_ln)?"""
+    return bool(_lib.lib().mvlpt_gemm_ln_supported(int(M), int(N)))
+
+
 def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid=None, alpha=1.0,
-         M=None, N=None, K=None, lda=None, ldw=None, ld_out=None, ld_aux=None):
-    """out[M,N] = epi(alpha * A[M,K] @ W[N,K]^T); see include/mvlpt_sm100.h:mvlpt_gemm."""
+         M=None, N=None, K=None, lda=None, ldw=None, ld_out=None, ld_aux=None, ln=None):
+    """out[M,N] = epi(alpha * A[M,K] @ W[N,K]^T); see include/mvlpt_sm100.h:mvlpt_gemm.
+    ln=(gamma, beta, h): also h = LayerNorm(out) * gamma + beta as fp16 (mvlpt_gemm_ln)."""
     _chk(A, torch.float16, "gemm A")
     _chk(W, torch.float16, "gemm W")
     M = A.shape[0] if M is None else M
@@ -83,14 +89,22 @@ def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid
         raise _lib.MvlptError("gemm out must be fp16 or fp32")
     d = GemmDesc(M, N, K, lda, ldw, ld_out, ld_aux, act, out_f32, float(alpha))
     t0 = PROFILER.begin() if PROFILER is not None else None
-    check(_lib.lib().mvlpt_gemm(byref(d), _p(A), _p(W), _p(bias), _p(aux_in), _p(aux_out), _p(resid), _p(out),
-                                _stream()), "mvlpt_gemm")
+    if ln is not None:
+        g_, b_, h_ = ln
+        _chk(h_, torch.float16, "gemm ln_out")
+        if aux is not None or alpha != 1.0:
+            raise _lib.MvlptError("gemm: the fused LayerNorm goes with the plain residual epilogue only")
+        check(_lib.lib().mvlpt_gemm_ln(byref(d), _p(A), _p(W), _p(bias), _p(resid), _p(out), _p(g_), _p(b_), _p(h_), LN_EPS,
+                                       _stream()), "mvlpt_gemm_ln")
+    else:
+        check(_lib.lib().mvlpt_gemm(byref(d), _p(A), _p(W), _p(bias), _p(aux_in), _p(aux_out), _p(resid), _p(out),
+                                    _stream()), "mvlpt_gemm")
     if t0 is not None:
         nbytes = 2.0 * (M * K + N * K) + (4.0 if out_f32 else 2.0) * M * N + (4.0 * M * N if resid is not None else 0.0) \
-            + (2.0 * M * N if aux is not None else 0.0)
+            + (2.0 * M * N if aux is not None else 0.0) + (2.0 * M * N if ln is not None else 0.0)
         PROFILER.end("gemm_f16_tn", t0, 2.0 * M * N * K, nbytes)
-        PROFILER.records.append((f"gemm[M={M},N={N},K={K},act={act},f32={out_f32},resid={int(resid is not None)}]",
-                                 *PROFILER.records[-1][1:]))
+        PROFILER.records.append((f"gemm[M={M},N={N},K={K},act={act},f32={out_f32},resid={int(resid is not None)}"
+                                 f"{',ln=1' if ln is not None else ''}]", *PROFILER.records[-1][1:]))
     return out
 
 
@@ -140,9 +154,12 @@ def embed_assemble(pe, cls, pos, gamma, beta, prompt, x0, B, G, v, d):
                                           v, d, LN_EPS, _stream()), "mvlpt_embed_assemble")
 
 
-def set_prompt_rows(x, prompt, B, L, v, d, drop_p=0.0, seed=0, slab=0):
-    check(_lib.lib().mvlpt_set_prompt_rows(_p(x), _p(prompt), int(prompt.dtype == torch.float16), B, L, v, d, float(drop_p),
-                                           int(seed), int(slab), _stream()), "mvlpt_set_prompt_rows")
+def set_prompt_rows(x, prompt, B, L, v, d, drop_p=0.0, seed=0, slab=0, ln=None):
+    """ln=(gamma, beta, h): also h[rows] = LayerNorm(new rows) (the fused-LayerNorm path, mvlpt_set_prompt_rows_ln)."""
+    g_, b_, h_ = ln if ln is not None else (None, None, None)
+    check(_lib.lib().mvlpt_set_prompt_rows_ln(_p(x), _p(prompt), int(prompt.dtype == torch.float16), B, L, v, d,
+                                              float(drop_p), int(seed), int(slab), _p(h_), _p(g_), _p(b_), LN_EPS,
+                                              _stream()), "mvlpt_set_prompt_rows")
 
 
 def dropout_keep(keep, B, v, d, drop_p, seed, slab):

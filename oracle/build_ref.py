@@ -1,10 +1,10 @@
 """Build recipe of `oracle/_ref/`: the UNMODIFIED reference hot path, byte-compiled where its sources lie.
 
-    python oracle/build_ref.py            # /root/reference -> oracle/_ref/{clip,trainers}/*.pyc (+ the BPE vocabulary)
+    python oracle/build_ref.py            # /root/reference -> oracle/_ref/{clip,trainers}/*.refpyc (+ the BPE vocabulary)
 
 The reference is pure Python (no native code, no build system), so "compiling" it means `py_compile` of
 the five modules the path imports — clip/{__init__,clip,model,simple_tokenizer}.py and trainers/mvlpt.py — read from
-/root/reference and written ONLY into oracle/_ref/ as sourceless `.pyc` files, next to the tokenizer's vocabulary data
+/root/reference and written ONLY into oracle/_ref/ as sourceless byte-code files (`*.refpyc`), next to the tokenizer's vocabulary data
 file it opens relative to its own location (clip/simple_tokenizer.py:10-12).  oracle/_ref/ is git-ignored (no reference
 source enters the history) but not gpurun-ignored, so the compiled reference travels to the GPU box, where
 /root/reference does not exist.  `__graft_entry__.build()` runs this when /root/reference is present.
@@ -29,13 +29,15 @@ REF = Path(os.environ.get("MVLPT_REFERENCE", "/root/reference"))
 
 MODULES = ["clip/__init__.py", "clip/clip.py", "clip/model.py", "clip/simple_tokenizer.py", "trainers/mvlpt.py"]
 DATA = ["clip/bpe_simple_vocab_16e6.txt.gz"]
+# compiled modules carry this suffix instead of ".pyc": snapshot tools (gpurun among them) drop *.pyc files
+SUFFIX = ".refpyc"
 
 
 def build_ref(ref: Path = REF, out: Path = OUT) -> Path:
     if not ref.exists():
         raise FileNotFoundError(f"{ref} is absent (GPU box?): oracle/_ref/ is built in the build container only")
     for rel in MODULES:
-        dst = out / Path(rel).with_suffix(".pyc")
+        dst = out / Path(rel).with_suffix(SUFFIX)
         dst.parent.mkdir(parents=True, exist_ok=True)
         py_compile.compile(str(ref / rel), cfile=str(dst), dfile=f"<reference>/{rel}", doraise=True)
     for rel in DATA:
@@ -47,7 +49,7 @@ def build_ref(ref: Path = REF, out: Path = OUT) -> Path:
 
 
 def available(out: Path = OUT) -> bool:
-    return all((out / Path(rel).with_suffix(".pyc")).exists() for rel in MODULES) and all((out / r).exists() for r in DATA)
+    return all((out / Path(rel).with_suffix(SUFFIX)).exists() for rel in MODULES) and all((out / r).exists() for r in DATA)
 
 
 def install_stubs(root: Path) -> None:
@@ -86,11 +88,38 @@ def install_stubs(root: Path) -> None:
         sys.path.insert(0, str(root))
 
 
+def _load_compiled(name: str, path: Path, package_dir: Path | None = None):
+    import importlib.machinery
+    import importlib.util
+    loader = importlib.machinery.SourcelessFileLoader(name, str(path))
+    spec = importlib.util.spec_from_file_location(name, str(path), loader=loader,
+                                                  submodule_search_locations=[str(package_dir)] if package_dir else None)
+    m = importlib.util.module_from_spec(spec)
+    sys.modules[name] = m
+    loader.exec_module(m)
+    return m
+
+
 def import_reference(root: Path = OUT):
-    """-> (clip.model module, trainers.mvlpt module) of the reference under `root`."""
+    """-> (clip.model module, trainers.mvlpt module) of the reference under `root`: the source tree (/root/reference), or
+    oracle/_ref, whose sourceless modules are loaded explicitly in dependency order (they are not named *.pyc)."""
+    root = Path(root)
     install_stubs(root)
     import importlib
-    return importlib.import_module("clip.model"), importlib.import_module("trainers.mvlpt")
+    if (root / "clip" / "model.py").exists():
+        return importlib.import_module("clip.model"), importlib.import_module("trainers.mvlpt")
+    pkg = types.ModuleType("clip")
+    pkg.__path__ = [str(root / "clip")]
+    pkg.__file__ = str(root / "clip" / ("__init__" + SUFFIX))
+    sys.modules["clip"] = pkg
+    model = _load_compiled("clip.model", root / "clip" / ("model" + SUFFIX))
+    pkg.model = model
+    pkg.simple_tokenizer = _load_compiled("clip.simple_tokenizer", root / "clip" / ("simple_tokenizer" + SUFFIX))
+    pkg.clip = _load_compiled("clip.clip", root / "clip" / ("clip" + SUFFIX))
+    for k in getattr(pkg.clip, "__all__", []):  # clip/__init__.py: `from .clip import *`
+        setattr(pkg, k, getattr(pkg.clip, k))
+    mv = _load_compiled("trainers.mvlpt", root / "trainers" / ("mvlpt" + SUFFIX))
+    return model, mv
 
 
 if __name__ == "__main__":

@@ -42,6 +42,44 @@ def test_gemm(M, N, K, act, resid, f32):
     assert _rel(out.float(), ref) < 2e-3
 
 
+@pytest.mark.parametrize("M,N,K,inplace", [
+    (256, 768, 768, False), (410, 768, 768, False), (515, 512, 2048, True), (1000, 1024, 1024, False),
+    (52480, 768, 768, True), (52480, 768, 3072, False), (25000, 512, 512, False), (300, 256, 64, False),
+    (41 * 256 + 7, 768, 768, False),  # more row blocks than CTA pairs is not needed for the ragged last block
+    (74 * 256 * 2 + 130, 512, 512, True),  # every pair owns several row blocks, the last one ragged
+])
+def test_gemm_with_fused_layernorm(M, N, K, inplace):
+    """mvlpt_gemm_ln: out = A.W^T + b + resid (fp32) and h = LayerNorm(out)*gamma+beta (fp16) from one kernel, against
+    torch's two-pass layer_norm of the same fp32 rows; rows with a large mean exercise the sum-of-squares statistics."""
+    from mvlpt_b200 import ops
+    assert ops.gemm_ln_supported(M, N)
+    assert not ops.gemm_ln_supported(255, N) and not ops.gemm_ln_supported(M, 128) and not ops.gemm_ln_supported(M, 1280)
+    torch.manual_seed(0)
+    dev = "cuda"
+    A = (torch.randn(M, K, device=dev) * 0.5).half()
+    W = (torch.randn(N, K, device=dev) * 0.05).half()
+    b = (torch.randn(N, device=dev) * 0.1).half()
+    r = torch.randn(M, N, device=dev) * 2
+    r[::7] += 6.0   # rows whose mean is several standard deviations from zero
+    gamma = torch.randn(N, device=dev) * 0.1 + 1
+    beta = torch.randn(N, device=dev) * 0.1
+    ref = A.float() @ W.float().t() + b.float() + r
+    out = r.clone() if inplace else torch.full((M, N), float("nan"), device=dev)
+    h = torch.full((M, N), float("nan"), device=dev, dtype=torch.half)
+    ops.gemm(A, W, out, bias=b, resid=out if inplace else r, ln=(gamma, beta, h))
+    assert not torch.isnan(out).any() and not torch.isnan(h).any()
+    assert _rel(out, ref) < 2e-3
+    # the LayerNorm of the rows the kernel itself produced: exact up to fp16 rounding of h
+    want = torch.nn.functional.layer_norm(out, (N,), gamma, beta, 1e-5)
+    assert _rel(h.float(), want) < 1.5e-3
+    # and identical (to fp16 rounding) to the stand-alone LayerNorm kernel on the same rows
+    h2 = torch.empty_like(h)
+    ops.ln_fwd(out, gamma, beta, h2, M, N)
+    assert (h.float() - h2.float()).abs().max() <= 2e-3 * want.abs().max()
+    with pytest.raises(Exception):
+        ops.gemm(A[:100], W, out[:100], bias=b, resid=r[:100], ln=(gamma, beta, h[:100]))
+
+
 @pytest.mark.parametrize("N,L,heads,causal", [(3, 197, 12, 0), (2, 205, 12, 0), (2, 50, 12, 0), (1, 257, 16, 0),
                                               (5, 77, 8, 1), (4, 20, 8, 1), (2, 1, 2, 0), (2, 16, 2, 1), (40, 205, 12, 0),
                                               (3, 130, 2, 1), (2, 64, 1, 0), (1, 272, 1, 0), (2, 256, 2, 0), (3, 128, 3, 1),
