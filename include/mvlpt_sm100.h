@@ -101,6 +101,11 @@ int mvlpt_ln_fwd(const void* x, const void* row_index, const void* gamma, const 
                  float eps, mvlpt_stream_t stream);
 int mvlpt_ln_bwd(const void* dy, const void* x, const void* row_index, const void* gamma, void* dx_stream, void* dx16,
                  int rows, int d, float eps, int accumulate, mvlpt_stream_t stream);
+/* hilo = 1: y is fp16 [rows, 2d] = [hi | lo], LN(x) = hi + lo to 2^-22: the A operand of a K = 2d mvlpt_gemm against
+ * [W | W], used for the pooled CLS / EOT rows so that the feature projection (trainers/mvlpt.py:91,128) does not see
+ * the fp16 rounding of its input.  hilo = 0 is mvlpt_ln_fwd. */
+int mvlpt_ln_fwd_hilo(const void* x, const void* row_index, const void* gamma, const void* beta, void* y, int rows, int d,
+                      float eps, int hilo, mvlpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Image stem (trainers/mvlpt.py:53-58 = clip/model.py:220-225; conv1 clip/model.py:207).
@@ -165,6 +170,11 @@ int mvlpt_ctx_grad(const void* dx0, int dx_f16, const void* ctx_pos, void* grad,
  * mvlpt_transpose_f16: out[c,r] = in[r,c], zero padded to ld_out — operand layout for the head dgrads.
  * ------------------------------------------------------------------------------------------------ */
 int mvlpt_l2norm_fwd(const void* x, void* y16, void* y32, void* inv_norm, int rows, int e, mvlpt_stream_t stream);
+/* Same, plus y16x3 fp16 [rows, 3e] (may be NULL): the split y = hi + lo laid out for ONE mvlpt_gemm of K = 3e that sums
+ * hi.hi' + hi.lo' + lo.hi' — the logit matmul (trainers/mvlpt.py:554) to fp32 accuracy on the fp16 tensor cores.
+ * pattern 0 = [hi | hi | lo] (image side, the A operand), pattern 1 = [hi | lo | hi] (text side, the W operand). */
+int mvlpt_l2norm_fwd_split(const void* x, void* y16, void* y32, void* inv_norm, void* y16x3, int pattern, int rows, int e,
+                           mvlpt_stream_t stream);
 int mvlpt_l2norm_bwd(const void* dy, const void* y32, const void* inv_norm, void* dx16, int rows, int e,
                      mvlpt_stream_t stream);
 int mvlpt_ce_fwd_bwd(void* logits, int ldc, const void* label, const void* soft, const void* task, const void* ranges,

@@ -46,6 +46,7 @@ struct GemmEpilogue {
     const float* ln_x;      // the fp32 output buffer itself (read back from L2 once its row block is complete)
     int ln_ldx;             // its row stride in elements
     float ln_eps;
+    int ln_dbg;             // tuning only (MVLPT_LN_DBG): 1 skip the normalisation pass, 2 skip the store-completion wait
 };
 
 constexpr int kGemmBM = 128;
@@ -677,7 +678,7 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     // ---- the 128 rows of this CTA are complete: finish LayerNorm (clip/model.py:153-159) ----
                     ln_stats[r * 2 + half] = make_float2(ln_s1, ln_s2);
                     ln_s1 = ln_s2 = 0.f;
-                    if (issuer) {
+                    if (issuer && !(ep.ln_dbg & 2)) {
                         tma_store_wait_all();  // the row block has reached L2 (completion, not just the smem reads)
                         asm volatile("fence.proxy.async.global;" ::: "memory");
                     }
@@ -686,7 +687,7 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                     const int nchunk = N >> 7;     // 128-column chunks of a row (N % 256 == 0, N <= 1024)
                     const float inv_n = 1.f / (float)N;
 #pragma unroll 1
-                    for (int i = 0; i < 16; i += 2) {
+                    for (int i = (ep.ln_dbg & 1) ? 16 : 0; i < 16; i += 2) {
                         const int r0 = ew * 16 + i;
                         const int gm0 = m0 + r0, gm1 = gm0 + 1;
                         float4 xa[8], xb[8];

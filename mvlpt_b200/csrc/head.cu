@@ -22,8 +22,11 @@ __device__ __forceinline__ float wmax(float v) {
 }
 
 // y = x / ||x||_2 per row (one warp per row)
+// y16x3 (optional, [rows, 3e]): the fp16 split v = hi + lo laid out for ONE tensor-core GEMM of K = 3e that evaluates
+// hi.hi' + hi.lo' + lo.hi' (the fp32 product up to the lo.lo' term, 2^-22 relative): pattern 0 writes [hi | hi | lo]
+// (the A operand), pattern 1 writes [hi | lo | hi] (the W operand).
 __global__ void l2norm_fwd_kernel(const float* __restrict__ x, __half* __restrict__ y16, float* __restrict__ y32,
-                                  float* __restrict__ inv_norm, int rows, int e) {
+                                  float* __restrict__ inv_norm, __half* __restrict__ y16x3, int pattern, int rows, int e) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= rows) return;
@@ -33,8 +36,16 @@ __global__ void l2norm_fwd_kernel(const float* __restrict__ x, __half* __restric
     const float inv = rsqrtf(wsum(s));
     for (int c = lane; c < e; c += 32) {
         const float v = xr[c] * inv;
+        const __half hi = __float2half_rn(v);
         y32[(size_t)r * e + c] = v;
-        y16[(size_t)r * e + c] = __float2half_rn(v);
+        y16[(size_t)r * e + c] = hi;
+        if (y16x3) {
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            __half* o = y16x3 + (size_t)r * 3 * e + c;
+            o[0] = hi;
+            o[e] = pattern ? lo : hi;
+            o[2 * e] = pattern ? hi : lo;
+        }
     }
     if (lane == 0) inv_norm[r] = inv;
 }
@@ -251,13 +262,18 @@ __global__ void sgd_kernel(T* __restrict__ p, T* __restrict__ buf, const float* 
 extern "C" {
 
 int mvlpt_l2norm_fwd(const void* x, void* y16, void* y32, void* inv_norm, int rows, int e, mvlpt_stream_t stream) {
+    return mvlpt_l2norm_fwd_split(x, y16, y32, inv_norm, nullptr, 0, rows, e, stream);
+}
+
+int mvlpt_l2norm_fwd_split(const void* x, void* y16, void* y32, void* inv_norm, void* y16x3, int pattern, int rows, int e,
+                           mvlpt_stream_t stream) {
     if (!x || !y16 || !y32 || !inv_norm) return fail(MVLPT_EINVAL, "mvlpt_l2norm_fwd: null argument");
     if (rows <= 0 || e <= 0) return fail(MVLPT_EINVAL, "mvlpt_l2norm_fwd: bad sizes");
     int rc = require_sm100();
     if (rc) return rc;
     l2norm_fwd_kernel<<<cdiv(rows, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
         static_cast<const float*>(x), static_cast<__half*>(y16), static_cast<float*>(y32),
-        static_cast<float*>(inv_norm), rows, e);
+        static_cast<float*>(inv_norm), static_cast<__half*>(y16x3), pattern, rows, e);
     return launched("l2norm_fwd");
 }
 

@@ -101,9 +101,11 @@ __device__ __forceinline__ void row_affine(Row& r, const float* g, const float* 
 }
 
 // ---------------------------------------------------------------- LayerNorm forward
+// hilo: y is [rows, 2d] = [hi | lo] with value = hi + lo in fp16 pairs (the operand of a K = 2d GEMM against [W | W]: the
+// pooled CLS / EOT rows enter the feature projection without the fp16 rounding of their LayerNorm output).
 __global__ void ln_fwd_kernel(const float* __restrict__ x, const int* __restrict__ row_index,
                               const float* __restrict__ gamma, const float* __restrict__ beta, __half* __restrict__ y,
-                              int rows, int d, float eps) {
+                              int rows, int d, float eps, int hilo) {
     pdl_sync();
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -114,7 +116,20 @@ __global__ void ln_fwd_kernel(const float* __restrict__ x, const int* __restrict
     float mean, rstd;
     row_stats(row, d, lane, eps, mean, rstd);
     row_affine(row, gamma, beta, d, lane, mean, rstd);
-    row_store_h(row, y + (size_t)r * d, d, lane);
+    if (!hilo) {
+        row_store_h(row, y + (size_t)r * d, d, lane);
+        return;
+    }
+    __half* yr = y + (size_t)r * 2 * d;
+    row_store_h(row, yr, d, lane);
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {  // lo = value - fp16(value)
+        row.v[i].x -= __half2float(__float2half_rn(row.v[i].x));
+        row.v[i].y -= __half2float(__float2half_rn(row.v[i].y));
+        row.v[i].z -= __half2float(__float2half_rn(row.v[i].z));
+        row.v[i].w -= __half2float(__float2half_rn(row.v[i].w));
+    }
+    row_store_h(row, yr + d, d, lane);
 }
 
 // ---------------------------------------------------------------- LayerNorm backward (gamma/beta frozen)
@@ -521,6 +536,11 @@ extern "C" {
 
 int mvlpt_ln_fwd(const void* x, const void* row_index, const void* gamma, const void* beta, void* y, int rows, int d,
                  float eps, mvlpt_stream_t stream) {
+    return mvlpt_ln_fwd_hilo(x, row_index, gamma, beta, y, rows, d, eps, 0, stream);
+}
+
+int mvlpt_ln_fwd_hilo(const void* x, const void* row_index, const void* gamma, const void* beta, void* y, int rows, int d,
+                      float eps, int hilo, mvlpt_stream_t stream) {
     if (!x || !gamma || !beta || !y) return fail(MVLPT_EINVAL, "mvlpt_ln_fwd: null argument");
     if (rows <= 0) return fail(MVLPT_EINVAL, "mvlpt_ln_fwd: rows must be positive");
     int rc = check_d(d, "mvlpt_ln_fwd");
@@ -528,7 +548,7 @@ int mvlpt_ln_fwd(const void* x, const void* row_index, const void* gamma, const 
     if ((rc = require_sm100())) return rc;
     MVLPT_CUDA_OK(launch_pdl(ln_fwd_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
                              static_cast<const float*>(x), static_cast<const int*>(row_index), static_cast<const float*>(gamma),
-                             static_cast<const float*>(beta), static_cast<__half*>(y), rows, d, eps));
+                             static_cast<const float*>(beta), static_cast<__half*>(y), rows, d, eps, hilo));
     return launched("ln_fwd");
 }
 

@@ -163,6 +163,7 @@ class ImageTower:
         self.ln_post_g, self.ln_post_b = f("visual.ln_post.weight"), f("visual.ln_post.bias")
         self.proj = sd["visual.proj"].detach().to(device=device, dtype=F16).contiguous()  # [d, e]
         self.proj_t = self.proj.t().contiguous()  # [e, d]
+        self.proj_t2 = torch.cat([self.proj_t, self.proj_t], dim=1).contiguous()  # [e, 2d]: against pooled [hi | lo]
         self.blocks = [BlockWeights(sd, f"visual.transformer.resblocks.{i}.", device) for i in range(self.layers)]
         self.device = device
         self._bufs: Dict[tuple, dict] = {}
@@ -180,7 +181,7 @@ class ImageTower:
                 patches=torch.empty(B * self.G, self.Kp, device=dev, dtype=F16),
                 pe=torch.empty(B * self.G, d, device=dev, dtype=F16),
                 cls_idx=(torch.arange(B, device=dev, dtype=I32) * L).contiguous(),
-                pooled=torch.empty(B, d, device=dev, dtype=F16),
+                pooled=torch.empty(B, 2 * d, device=dev, dtype=F16),
                 feat=torch.empty(B, self.e, device=dev, dtype=F32),
                 dpool=torch.empty(B, d, device=dev, dtype=F16) if train else None,
             )
@@ -229,8 +230,10 @@ class ImageTower:
             last = a.x_out(l)
         bf["final"] = last
         bf["run"] = run
-        ops.ln_fwd(last, self.ln_post_g, self.ln_post_b, bf["pooled"], B, self.d, row_index=bf["cls_idx"])
-        ops.gemm(bf["pooled"], self.proj_t, bf["feat"])
+        # the pooled row goes into the projection as an fp16 pair hi + lo (K = 2d): the feature is the last thing the
+        # tower computes, nothing downstream averages the rounding of its input away
+        ops.ln_fwd(last, self.ln_post_g, self.ln_post_b, bf["pooled"], B, self.d, row_index=bf["cls_idx"], hilo=True)
+        ops.gemm(bf["pooled"], self.proj_t2, bf["feat"])
         return bf["feat"]
 
     def backward(self, dfeat16: torch.Tensor, B: int, v: int, n_deep: Optional[int], grad_vpt: torch.Tensor,
@@ -266,6 +269,7 @@ class TextTower:
         self.ln_g, self.ln_b = f("ln_final.weight"), f("ln_final.bias")
         self.proj = sd["text_projection"].detach().to(device=device, dtype=F16).contiguous()  # [d_t, e]
         self.proj_t = self.proj.t().contiguous()
+        self.proj_t2 = torch.cat([self.proj_t, self.proj_t], dim=1).contiguous()  # [e, 2d]: against pooled [hi | lo]
         self.blocks = [BlockWeights(sd, f"transformer.resblocks.{i}.", device) for i in range(self.layers)]
         self.device = device
         self._bufs: Dict[tuple, dict] = {}
@@ -279,7 +283,7 @@ class TextTower:
                     b.ensure_transposed()
             self._bufs[key] = dict(
                 act=TowerBuffers(C, Lt, d, self.heads, self.layers, train, dev),
-                pooled=torch.empty(C, d, device=dev, dtype=F16),
+                pooled=torch.empty(C, 2 * d, device=dev, dtype=F16),
                 feat=torch.empty(C, self.e, device=dev, dtype=F32),
                 dpool=torch.empty(C, d, device=dev, dtype=F16) if train else None,
             )
@@ -305,8 +309,8 @@ class TextTower:
             h_ready = block_forward(self.blocks[l], a, l, causal=True, h_ready=h_ready,
                                     next_ln=None if nxt is None else (nxt.ln1_g, nxt.ln1_b))
         bf["final"] = a.x_out(self.layers - 1)
-        ops.ln_fwd(bf["final"], self.ln_g, self.ln_b, bf["pooled"], N, d, row_index=eot_rows)
-        ops.gemm(bf["pooled"], self.proj_t, bf["feat"])
+        ops.ln_fwd(bf["final"], self.ln_g, self.ln_b, bf["pooled"], N, d, row_index=eot_rows, hilo=True)
+        ops.gemm(bf["pooled"], self.proj_t2, bf["feat"])
         return bf["feat"]
 
     def backward_to_input(self, dfeat16: torch.Tensor, N: int, Lt: int, eot_rows: torch.Tensor) -> torch.Tensor:
@@ -345,7 +349,7 @@ class LogitHead:
             dev, e = self.device, self.e
             z = lambda *s, dt=F16: torch.zeros(*s, device=dev, dtype=dt)
             self._tbufs[C] = dict(t16=z(C, e), t32=z(C, e, dt=F32), t_inv=z(C, dt=F32), t16_t=z(e, _round_up(C, 8)),
-                                  dt32=z(C, e, dt=F32), dtfeat16=z(C, e))
+                                  t16x3=z(C, 3 * e), dt32=z(C, e, dt=F32), dtfeat16=z(C, e))
         return self._tbufs[C]
 
     def buffers(self, B: int, C: int) -> dict:
@@ -356,7 +360,7 @@ class LogitHead:
             z = lambda *s, dt=F16: torch.zeros(*s, device=dev, dtype=dt)
             self._bufs[key] = dict(
                 ldc=ldc, ldb=ldb,
-                i16=z(B, e), i32=z(B, e, dt=F32), i_inv=z(B, dt=F32),
+                i16=z(B, e), i32=z(B, e, dt=F32), i_inv=z(B, dt=F32), i16x3=z(B, 3 * e),
                 logits=z(B, ldc, dt=F32), dz16=z(B, ldc), loss_rows=z(B, dt=F32), pred=z(B, dt=I32),
                 hit=z(B, dt=I32), metrics=z(2, dt=F32),
                 dz16_t=z(C, ldb), i16_t=z(e, ldb),
@@ -368,13 +372,15 @@ class LogitHead:
     def normalize_text(self, txt_feat: torch.Tensor):
         C = txt_feat.shape[0]
         bf = self.text_buffers(C)
-        ops.l2norm_fwd(txt_feat, bf["t16"], bf["t32"], bf["t_inv"], C, self.e)
+        ops.l2norm_fwd(txt_feat, bf["t16"], bf["t32"], bf["t_inv"], C, self.e, y16x3=bf["t16x3"], pattern=1)
 
     def logits(self, img_feat: torch.Tensor, C: int) -> torch.Tensor:
         B = img_feat.shape[0]
         bf = self.buffers(B, C)
-        ops.l2norm_fwd(img_feat, bf["i16"], bf["i32"], bf["i_inv"], B, self.e)
-        ops.gemm(bf["i16"], bf["t16"], bf["logits"], alpha=self.s, N=C)
+        # logits = s * i.t with both normalised features split into fp16 pairs: [hi|hi|lo] . [hi|lo|hi] over K = 3e is
+        # hi.hi + hi.lo + lo.hi, the fp32 product to 2^-22 — the cosine itself is not rounded to fp16 operands
+        ops.l2norm_fwd(img_feat, bf["i16"], bf["i32"], bf["i_inv"], B, self.e, y16x3=bf["i16x3"], pattern=0)
+        ops.gemm(bf["i16x3"], bf["t16x3"], bf["logits"], alpha=self.s, N=C)
         return bf["logits"]
 
     def backward(self, B: int, C: int, need_img: bool, need_txt: bool):

@@ -123,10 +123,11 @@ def fmha_bwd(qkv, o, d_o, lse, dqkv, N, L, d, heads, causal):
         PROFILER.end("fmha_bwd", t0, 8.0 * N * L * L * d, 2.0 * N * L * 8 * d + 4.0 * N * heads * L)
 
 
-def ln_fwd(x, gamma, beta, y, rows, d, row_index=None):
+def ln_fwd(x, gamma, beta, y, rows, d, row_index=None, hilo=False):
+    """hilo: y is [rows, 2d] = [hi | lo] (mvlpt_ln_fwd_hilo)."""
     t0 = PROFILER.begin() if PROFILER is not None else None
-    check(_lib.lib().mvlpt_ln_fwd(_p(x), _p(row_index), _p(gamma), _p(beta), _p(y), rows, d, LN_EPS, _stream()),
-          "mvlpt_ln_fwd")
+    check(_lib.lib().mvlpt_ln_fwd_hilo(_p(x), _p(row_index), _p(gamma), _p(beta), _p(y), rows, d, LN_EPS, int(hilo),
+                                       _stream()), "mvlpt_ln_fwd")
     if t0 is not None:
         PROFILER.end("ln_fwd", t0, 0.0, 6.0 * rows * d)
 
@@ -184,8 +185,9 @@ def ctx_grad(dx0, ctx_pos, grad, C, Lt, n_ctx, d, csc, inv_scale):
                                     int(csc), float(inv_scale), _stream()), "mvlpt_ctx_grad")
 
 
-def l2norm_fwd(x, y16, y32, inv_norm, rows, e):
-    check(_lib.lib().mvlpt_l2norm_fwd(_p(x), _p(y16), _p(y32), _p(inv_norm), rows, e, _stream()), "mvlpt_l2norm_fwd")
+def l2norm_fwd(x, y16, y32, inv_norm, rows, e, y16x3=None, pattern=0):
+    check(_lib.lib().mvlpt_l2norm_fwd_split(_p(x), _p(y16), _p(y32), _p(inv_norm), _p(y16x3), int(pattern), rows, e,
+                                            _stream()), "mvlpt_l2norm_fwd")
 
 
 def l2norm_bwd(dy, y32, inv_norm, dx16, rows, e):

@@ -169,3 +169,44 @@ def synth_token_ids(n_cls: int, n_ctx: int, context_length: int = 77, seed: int 
         toks[c, :len(row)] = torch.tensor(row)
         name_lens.append(nl)
     return toks, name_lens
+
+
+class SyntheticDataManager:
+    """The attribute surface the MVLPT trainer reads from a Dassl DataManager (`dataset.classnames`,
+    `lab2cname`, `num_classes`, `num_source_domains`, `train_loader_x`, `val_loader`, `test_loader`) over synthetic
+    batches in the reference's CoOp-data format {'img', 'label', 'domain'} (trainers/mvlpt.py:953-968).  Loaders are
+    lists of pinned host batches; the last test batch is ragged, as Dassl's `drop_last=False` test loaders are.
+    Offline stand-in for the reference's dataset plumbing (out of scope): used by
+    `python -m mvlpt_b200.train --synthetic`, tests and benchmarks."""
+
+    def __init__(self, arch: str, n_classes: int, train_batches: int = 4, batch_size: int = 8, test_images: int = 20,
+                 test_batch_size: int = 8, seed: int = 0, pin: bool = True, half: bool = True):
+        import types
+        res = ARCHS[arch]["image_resolution"]
+        names = [f"class{c}" for c in range(n_classes)]
+        self.dataset = types.SimpleNamespace(classnames=names)
+        self.lab2cname = {i: n for i, n in enumerate(names)}
+        self.num_classes = n_classes
+        self.num_source_domains = 1
+
+        def batch(n, s):
+            img = synth_images(n, res, seed=s)
+            img = img.half() if half else img
+            g = torch.Generator().manual_seed(31 * s + 7)
+            lab = torch.randint(0, n_classes, (n,), generator=g)
+            if pin and torch.cuda.is_available():
+                img, lab = img.pin_memory(), lab.pin_memory()
+            return {"img": img, "label": lab, "domain": torch.zeros(n, dtype=torch.long)}
+
+        def split(total, bs, s0):
+            out, done = [], 0
+            while done < total:
+                n = min(bs, total - done)
+                out.append(batch(n, s0 + len(out)))
+                done += n
+            return out
+
+        self.train_loader_x = [batch(batch_size, 1000 * seed + i) for i in range(train_batches)]
+        self.train_loader_u = None
+        self.val_loader = split(test_images, test_batch_size, 1000 * seed + 500)
+        self.test_loader = split(test_images, test_batch_size, 1000 * seed + 700)

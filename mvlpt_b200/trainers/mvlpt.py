@@ -837,6 +837,10 @@ class CustomCLIP(nn.Module):
 # Trainer (trainers/mvlpt.py:827-1125).  The reference subclasses Dassl's TrainerX; Dassl is not installable here,
 # so the handful of inherited members it uses are provided by this class itself.
 # ---------------------------------------------------------------------------------------------------------------
+from .runtime import TRAINER_REGISTRY  # noqa: E402
+
+
+@TRAINER_REGISTRY.register()
 class MVLPT:
     """Drop-in for the reference's `MVLPT(TrainerX)`: same cfg keys, same method names, same batch formats, same
     `forward_backward -> {"loss", "acc"[, "num_tasks"]}` contract.  One process per GPU; with torch.distributed
@@ -856,6 +860,8 @@ class MVLPT:
         self._models, self._optims, self._scheds = OrderedDict(), OrderedDict(), OrderedDict()
         self.epoch, self.start_epoch = 0, 0
         self.max_epoch = cfg.OPTIM.MAX_EPOCH
+        self.output_dir = getattr(cfg, "OUTPUT_DIR", "")
+        self.best_result = -float("inf")
         self.batch_idx, self.num_batches = 0, 1
         self._clip_state_dict = clip_state_dict
         self._tok = (tokenized_prompts, name_lens)
@@ -1109,17 +1115,53 @@ class MVLPT:
         return self._optims[self.get_model_names(names)[0]].param_groups[0]["lr"]
 
     def save_model(self, epoch, directory, is_best=False, val_result=None, model_name=""):
-        """Dassl's checkpoint layout: <dir>/<name>/model.pth.tar-<epoch> (+ model-best.pth.tar)."""
+        """Dassl's TrainerBase.save_model -> save_checkpoint (upstream): `epoch` is the 0-based epoch just finished; the file
+        is <dir>/<name>/model.pth.tar-<epoch+1> (or `model_name`), the dict stores epoch + 1, and a text file `checkpoint`
+        next to it names the newest one (what --resume reads).  Keys: state_dict / epoch / optimizer / scheduler /
+        val_result (scripts/avg_ckpt.py:21-66 reads the same)."""
         import os
         import os.path as osp
         for name in self.get_model_names():
+            sched = self._scheds[name]
             ckpt = {"state_dict": {k: v.detach().cpu() for k, v in self._models[name].state_dict().items()},
-                    "epoch": epoch, "optimizer": self._optims[name].state_dict(), "val_result": val_result}
-            os.makedirs(osp.join(directory, name), exist_ok=True)
-            fpath = osp.join(directory, name, model_name or f"model.pth.tar-{epoch}")
-            torch.save(ckpt, fpath)
+                    "epoch": epoch + 1, "optimizer": self._optims[name].state_dict(),
+                    "scheduler": None if sched is None else sched.state_dict(), "val_result": val_result}
+            save_dir = osp.join(directory, name)
+            os.makedirs(save_dir, exist_ok=True)
+            fname = model_name or f"model.pth.tar-{epoch + 1}"
+            torch.save(ckpt, osp.join(save_dir, fname))
+            with open(osp.join(save_dir, "checkpoint"), "w") as f:
+                f.write(fname + "\n")
             if is_best:
-                torch.save(ckpt, osp.join(directory, name, "model-best.pth.tar"))
+                torch.save(ckpt, osp.join(save_dir, "model-best.pth.tar"))
+
+    def resume_model_if_exist(self, directory) -> int:
+        """Dassl's TrainerBase.resume_model_if_exist (upstream; reached through --resume, train.py:55-56): if every
+        registered model has a `checkpoint` file under <directory>/<name>/, restore parameters, optimiser and scheduler
+        from the checkpoint it names and return the epoch to continue from; else 0."""
+        import os.path as osp
+        names = self.get_model_names()
+        if not directory or not all(osp.exists(osp.join(directory, n, "checkpoint")) for n in names):
+            if directory:
+                print("No checkpoint found, train from scratch")
+            return 0
+        start = 0
+        for name in names:
+            with open(osp.join(directory, name, "checkpoint")) as f:
+                fname = f.readline().strip()
+            path = osp.join(directory, name, fname)
+            ckpt = torch.load(path, map_location="cpu", weights_only=False)
+            print('Loading checkpoint from "{}"'.format(path))
+            self._models[name].load_state_dict(ckpt["state_dict"], strict=False)
+            self._optims[name].load_state_dict(ckpt["optimizer"])
+            for k, v in self._optims[name].bufs.items():
+                self._optims[name].bufs[k] = v.to(self.device)
+            if ckpt.get("scheduler") is not None and self._scheds[name] is not None:
+                self._scheds[name].load_state_dict(ckpt["scheduler"])
+            start = int(ckpt["epoch"])
+            print("Previous epoch: {}".format(start))
+        self.model._txt_cache_valid = False
+        return start
 
     def run_epoch(self):
         self.set_model_mode("train")
@@ -1137,8 +1179,57 @@ class MVLPT:
             last = self.forward_backward(batch)
         return last
 
+    # ---- Dassl's epoch loop (SimpleTrainer.before_train / after_epoch / after_train, upstream; train.py:219) -----------
+    def before_train(self):
+        directory = getattr(self.cfg, "RESUME", "") or self.output_dir
+        self.start_epoch = self.resume_model_if_exist(directory)
+
+    def after_epoch(self):
+        last_epoch = (self.epoch + 1) == self.max_epoch
+        do_test = not getattr(self.cfg.TEST, "NO_TEST", False)
+        freq = getattr(self.cfg.TRAIN, "CHECKPOINT_FREQ", 0)
+        meet_checkpoint_freq = (self.epoch + 1) % freq == 0 if freq > 0 else False
+        if do_test and self.cfg.TEST.FINAL_MODEL == "best_val" and self.val_loader is not None:
+            curr_result = self.test(split="val")
+            if curr_result > self.best_result:
+                self.best_result = curr_result
+                if self.output_dir:
+                    self.save_model(self.epoch, self.output_dir, val_result=curr_result, model_name="model-best.pth.tar")
+        if (meet_checkpoint_freq or last_epoch) and self.output_dir:
+            self.save_model(self.epoch, self.output_dir)
+
+    def after_train(self):
+        print("Finish training")
+        if getattr(self.cfg.TEST, "NO_TEST", False) or self.test_loader is None:
+            return None
+        if self.cfg.TEST.FINAL_MODEL == "best_val" and self.output_dir and self.val_loader is not None:
+            print("Deploy the model with the best val performance")
+            self.load_model(self.output_dir)
+        else:
+            print("Deploy the last-epoch model")
+        return self.test()
+
     def train(self):
+        """Dassl's TrainerBase.train (upstream): before_train, then per epoch run_epoch + after_epoch, then after_train.
+        Returns the last step's loss summary."""
         last = None
+        self.before_train()
         for self.epoch in range(self.start_epoch, self.max_epoch):
             last = self.run_epoch()
+            self.after_epoch()
+        self.final_result = self.after_train()
         return last
+
+
+# When Dassl is importable (an MVLPT checkout with its dependencies), put this trainer into ITS registry as well, under
+# the reference's name (`@TRAINER_REGISTRY.register() class MVLPT(TrainerX)`, trainers/mvlpt.py:827-828), so that
+# `--trainer MVLPT` in the reference's own train.py resolves here.  If the reference's trainers/mvlpt.py was imported
+# first the name is taken: leave it.
+try:  # pragma: no cover - dassl is not installable in this image
+    from dassl.engine import TRAINER_REGISTRY as _DASSL_REGISTRY
+    try:
+        _DASSL_REGISTRY.register()(MVLPT)
+    except (KeyError, AssertionError):
+        pass
+except ImportError:
+    pass

@@ -27,6 +27,7 @@ def default_cfg() -> NS:
     """Defaults of the keys the hot path reads (train.py:118-169; Dassl defaults for OPTIM)."""
     return NS(
         TRAINER=NS(
+            NAME="",
             MVLPT=NS(PREC="fp16", PROJECT_METHOD="transformer", PROJECT_DIM=128,
                      VPT=NS(N_CTX=0, CSC=False, CTX_INIT="", DROPOUT=0.0, PROJECT=-1, DEEP=True),
                      COOP=NS(N_CTX=0, CSC=False, CTX_INIT="", CLASS_TOKEN_POSITION="middle"),
@@ -40,12 +41,40 @@ def default_cfg() -> NS:
         OPTIM=NS(NAME="sgd", LR=0.002, MAX_EPOCH=200, LR_SCHEDULER="cosine", WARMUP_EPOCH=1, WARMUP_TYPE="constant",
                  WARMUP_CONS_LR=1e-5, MOMENTUM=0.9, WEIGHT_DECAY=5e-4, SGD_DAMPNING=0, SGD_NESTEROV=False),
         DATASET=NS(COOP=False, MULTITASK=False, MULTITASK_LABEL_PERTASK=False, MULTITASK_EVALKEY="average", NAME="",
-                   DATASET=""),
+                   DATASET="", ROOT="", NUM_SHOTS=-1, NUM_SAMPLES_PER_CLASS=20, RANDOM_SEED_SAMPLING=1,
+                   SUBSAMPLE_CLASSES="all", SOURCE_DOMAINS=(), TARGET_DOMAINS=()),
         DATALOADER=NS(TRAIN_X=NS(BATCH_SIZE=32), TEST=NS(BATCH_SIZE=100), NUM_WORKERS=8),
-        TEST=NS(SPLIT="test", FINAL_MODEL="last_step"),
-        TRAIN=NS(PRINT_FREQ=5),
-        OUTPUT_DIR="", VERBOSE=False, USE_CUDA=True, SEED=-1,
+        TEST=NS(SPLIT="test", FINAL_MODEL="last_step", NO_TEST=False),
+        TRAIN=NS(PRINT_FREQ=5, CHECKPOINT_FREQ=0),
+        OUTPUT_DIR="", RESUME="", VERBOSE=False, USE_CUDA=True, SEED=-1,
     )
+
+
+class Registry:
+    """dassl.engine.TRAINER_REGISTRY's surface (upstream: a fvcore-style name -> class table): `register()` is a class
+    decorator, `get(name)` looks a trainer up (train.py:208 build_trainer -> TRAINER_REGISTRY.get(cfg.TRAINER.NAME))."""
+
+    def __init__(self, name: str):
+        self._name, self._obj = name, {}
+
+    def register(self, obj=None, force: bool = False):
+        def deco(cls):
+            if cls.__name__ in self._obj and not force:
+                raise KeyError(f"{cls.__name__} is already registered in {self._name}")
+            self._obj[cls.__name__] = cls
+            return cls
+        return deco if obj is None else deco(obj)
+
+    def get(self, name: str):
+        if name not in self._obj:
+            raise KeyError(f"{name!r} is not registered in {self._name}; available: {sorted(self._obj)}")
+        return self._obj[name]
+
+    def registered_names(self):
+        return list(self._obj)
+
+
+TRAINER_REGISTRY = Registry("TRAINER")
 
 
 def _merge(node: NS, d: dict, path: str = ""):
@@ -160,6 +189,13 @@ class ConstantWarmupCosine:
 
     def get_last_lr(self):
         return [self.optim.lr]
+
+    def state_dict(self):
+        return dict(last_epoch=self.last_epoch)
+
+    def load_state_dict(self, sd):
+        self.last_epoch = int(sd["last_epoch"])
+        self._apply()
 
 
 def build_optimizer(named_params, optim_cfg) -> PromptSGD:

@@ -221,3 +221,53 @@ def test_reference_yaml_files_load_unchanged_and_select_the_transform_stack():
         assert build_transform(cfg, False).mode == "test"
     with pytest.raises(NotImplementedError):  # Dassl's own default interpolation is bilinear: not what MVLPT runs with
         build_transform(R.default_cfg(), True)
+
+
+def test_cli_config_precedence_matches_train_py():
+    """train.py:171-191: defaults <- dataset YAML <- trainer YAML <- named arguments <- free KEY VALUE options; the flag
+    set is the reference's (train.py:223-293)."""
+    from mvlpt_b200 import train as T
+    import tempfile
+    with tempfile.NamedTemporaryFile("w", suffix=".yaml", delete=False) as f:
+        f.write("OPTIM:\n  LR: 0.5\n  MAX_EPOCH: 7\nMODEL:\n  BACKBONE:\n    NAME: \"ViT-B/16\"\nINPUT:\n  SIZE: (224, 224)\n")
+        path = f.name
+    a = T.build_parser().parse_args(["--trainer", "MVLPT", "--config-file", path, "--output-dir", "/tmp/x", "--seed", "3",
+                                     "--multi-task", "--multi-task-label_pertask", "--dataset-coop", "--cut-contextlen",
+                                     "--backbone", "ViT-B/32", "--resume", "/tmp/r", "--shots", "5",
+                                     "--multi-task-evalkey", "dtd",
+                                     "OPTIM.MAX_EPOCH", "9", "TRAINER.MVLPT.COOP.N_CTX", "16", "TEST.FINAL_MODEL", "best_val"])
+    c = T.setup_cfg(a)
+    assert c.OPTIM.LR == 0.5 and c.OPTIM.MAX_EPOCH == 9          # YAML, then overridden by the free option
+    assert c.MODEL.BACKBONE.NAME == "ViT-B/32"                   # named argument beats the YAML
+    assert c.TRAINER.NAME == "MVLPT" and c.OUTPUT_DIR == "/tmp/x" and c.RESUME == "/tmp/r" and c.SEED == 3
+    assert c.DATASET.MULTITASK and c.DATASET.MULTITASK_LABEL_PERTASK and c.DATASET.COOP and c.TRAINER.CUT_CONTEXTLEN
+    assert c.DATASET.NUM_SHOTS == 5 and c.DATASET.MULTITASK_EVALKEY == "dtd" and c.DATASET.RANDOM_SEED_SAMPLING == 3
+    assert c.TRAINER.MVLPT.COOP.N_CTX == 16 and c.TEST.FINAL_MODEL == "best_val" and tuple(c.INPUT.SIZE) == (224, 224)
+    # defaults of extend_cfg (train.py:130-169)
+    d = T.setup_cfg(T.build_parser().parse_args([]))
+    M = d.TRAINER.MVLPT
+    assert (M.PREC, M.PROJECT_METHOD, M.PROJECT_DIM, M.VPT.N_CTX, M.VPT.DEEP, M.COOP.CLASS_TOKEN_POSITION) == \
+        ("fp16", "transformer", 128, 0, True, "middle")
+    assert not d.TRAINER.CUT_CONTEXTLEN and d.TRAINER.ACT_CKPT == 1 and d.DATASET.MULTITASK_EVALKEY == "average"
+
+
+def test_trainer_registry_resolves_mvlpt():
+    from mvlpt_b200.trainers.runtime import TRAINER_REGISTRY
+    from mvlpt_b200.trainers.mvlpt import MVLPT
+    assert TRAINER_REGISTRY.get("MVLPT") is MVLPT
+    with pytest.raises(KeyError):
+        TRAINER_REGISTRY.get("NoSuchTrainer")
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/configs/trainers/MVLPT"), reason="reference checkout not present")
+def test_cli_reads_the_reference_yaml_unchanged():
+    from mvlpt_b200 import train as T
+    a = T.build_parser().parse_args(["--trainer", "MVLPT", "--config-file",
+                                     "/root/reference/configs/trainers/MVLPT/vit_b16.yaml", "--dataset-coop", "--multi-task",
+                                     "TRAINER.MVLPT.VPT.N_CTX", "8", "TRAINER.MVLPT.COOP.N_CTX", "8",
+                                     "TRAINER.MVLPT.COOP.CLASS_TOKEN_POSITION", "middle", "TRAINER.MVLPT.COOP.CSC", "False",
+                                     "TEST.NO_TEST", "False", "TEST.FINAL_MODEL", "best_val", "TRAINER.CUT_CONTEXTLEN", "True"])
+    c = T.setup_cfg(a)   # the option list of scripts/mvlpt/main_mt_coopdata_cut.sh:30-47
+    assert c.OPTIM.LR == 0.002 and c.OPTIM.MAX_EPOCH == 200 and c.OPTIM.WARMUP_CONS_LR == 1e-5
+    assert c.DATALOADER.TRAIN_X.BATCH_SIZE == 32 and c.DATALOADER.TEST.BATCH_SIZE == 100
+    assert c.TRAINER.MVLPT.COOP.CSC is False and c.TEST.NO_TEST is False and c.TRAINER.CUT_CONTEXTLEN is True

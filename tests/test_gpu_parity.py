@@ -1,19 +1,40 @@
 """GPU parity: the CUDA path (through the C ABI, via the reference-API mirror) against the CPU oracle on the same
 seeded inputs and against the golden fixtures generated from the reference itself (oracle/gen_golden.py).
 
-Tolerances: the reference's OWN fp16 path sits 2.7e-3 (logits) / 2e-2 (gradients) away from exact
-arithmetic; BASELINE.json asks 1e-3 fp16-relative.  Our kernels keep fp32 accumulators and an fp32 residual stream;
-what remains is the fp16 rounding of GEMM operands.  Bars, normwise-max relative error against the fp32 reference:
-  logits  <= 3e-3 (tiny random-init models: features ~N(0,1) make this the noise floor of fp16 operands)
-  grads   <= 2e-2 and argmax bit-exact on every sample whose fp32 top-2 margin exceeds 4 fp16 ulps.
+Bars (normwise-max relative error  max|a-b| / max|b|  against the reference's fp32 run; BASELINE.json north star:
+1e-3 fp16-relative; SURVEY.md App. A: gradients 5e-3, and never worse than the reference's own fp16 path):
+
+  logits     <= 1e-3, or — where fp16 operand rounding makes that unreachable — <= the error of the reference's OWN fp16 run
+             of the same step (`ref16_logits` in the fixture) with 50 % slack for the spread between two independent fp16
+             evaluations; never above 2.5e-3
+  gradients  <= 5e-3, or <= 1.5 x the reference's own fp16 error of that gradient (`ref16_grads`)
+  argmax     bit-exact on every sample whose fp32 top-2 margin exceeds 4 fp16 ulps.
+
+The measured numbers per fixture are committed in profiles/r02_parity_report.json (tools/gpu_parity_report.py): full-size
+fixtures sit at 0.2-1.9e-3 (logits) against 1.4-7.0e-3 for the reference's fp16 path.  CoCoOp's first meta-net layer
+is the one ill-conditioned gradient: the oracle ITSELF moves it by 1.2e-2 when only the token embeddings are rounded to
+fp16 (what PREC="fp16" mandates, trainers/mvlpt.py:307), so it is held to 5 x its ref16 error instead.
 """
 import pytest
 import torch
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_TOL = 3e-3
-GRAD_TOL = 2e-2
+LOGIT_TOL, LOGIT_CAP = 1e-3, 2.5e-3
+GRAD_TOL = 5e-3
+REF16_SLACK = 1.5
+
+
+def logit_bar(ref16_err=None):
+    return LOGIT_TOL if ref16_err is None else min(LOGIT_CAP, max(LOGIT_TOL, REF16_SLACK * ref16_err))
+
+
+def grad_bar(name, ref16_err=None):
+    if ref16_err is None:
+        return GRAD_TOL
+    slack = 5.0 if name.startswith("meta_net.linear1") else REF16_SLACK
+    return max(GRAD_TOL, slack * ref16_err)
+
 
 TINY = ["tiny_coop_end", "tiny_coop_middle_cut", "tiny_coop_front_csc", "tiny_vpt_shallow", "tiny_vpt_deep",
         "tiny_vpt_deep_taskmask_soft", "tiny_upt_identity", "tiny_upt_transformer", "tiny_cocoop", "tiny_cocoop_vpt_deep",
@@ -34,9 +55,20 @@ def _run(name, prec):
     return model, fx, case, sd, image, pp, upt, logits, loss_rows.cpu(), pred.cpu(), {k: g.cpu() for k, g in grads.items()}
 
 
-def _check_against(fx_logits, fx_loss, fx_grads, margin, logits, loss_rows, pred, grads):
+def _ref16_errors(fx):
+    """Errors of the reference's own fp16 run against its fp32 run: (logits, {gradient name: error})."""
     from tests.helpers import rel_err
-    assert rel_err(logits, fx_logits) <= LOGIT_TOL
+    if "ref16_logits" not in fx:
+        return None, {}
+    return (rel_err(fx["ref16_logits"], fx["logits"]),
+            {k: rel_err(g.reshape(fx["grads"][k].shape), fx["grads"][k]) for k, g in fx["ref16_grads"].items()})
+
+
+def _check_against(fx_logits, fx_loss, fx_grads, margin, logits, loss_rows, pred, grads, ref16=(None, {})):
+    from tests.helpers import rel_err
+    r16_logits, r16_grads = ref16
+    le = rel_err(logits, fx_logits)
+    assert le <= logit_bar(r16_logits), f"logits {le:.2e} > bar {logit_bar(r16_logits):.2e} (reference fp16: {r16_logits})"
     assert abs(float(loss_rows.mean()) - float(fx_loss)) <= 5e-3 * max(1.0, abs(float(fx_loss)))
     ulp = 9.8e-4 * fx_logits.abs().max()
     safe = margin > 4 * ulp
@@ -44,10 +76,8 @@ def _check_against(fx_logits, fx_loss, fx_grads, margin, logits, loss_rows, pred
     assert torch.equal(pred.long()[safe], fx_logits.argmax(-1)[safe])
     for k, g in fx_grads.items():
         assert k in grads, f"missing gradient {k}"
-        # CoCoOp's first meta-net layer sits behind a ReLU fed by the (fp16-noisy) image features and behind the whole
-        # text-tower backward: its gradient is a heavily cancelling sum (measured 0.4-3.2e-2; everything else <= 1e-2)
-        tol = 5e-2 if k.startswith("meta_net.linear1") else GRAD_TOL
-        assert rel_err(grads[k].reshape(g.shape), g) <= tol, k
+        ge, bar = rel_err(grads[k].reshape(g.shape), g), grad_bar(k, r16_grads.get(k))
+        assert ge <= bar, f"gradient {k}: {ge:.2e} > bar {bar:.2e} (reference fp16: {r16_grads.get(k)})"
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
@@ -55,7 +85,8 @@ def _check_against(fx_logits, fx_loss, fx_grads, margin, logits, loss_rows, pred
 def test_step_matches_reference_golden(name, prec):
     """logits, loss, argmax and every prompt gradient vs the fixture produced by the reference's own CustomCLIP."""
     model, fx, case, sd, image, pp, upt, logits, loss_rows, pred, grads = _run(name, prec)
-    _check_against(fx["logits"], fx["loss"], fx["grads"], fx["top2_margin"], logits, loss_rows, pred, grads)
+    _check_against(fx["logits"], fx["loss"], fx["grads"], fx["top2_margin"], logits, loss_rows, pred, grads,
+                   ref16=_ref16_errors(fx))
 
 
 @pytest.mark.parametrize("name", TINY)
@@ -84,8 +115,9 @@ def test_step_matches_oracle_on_fresh_inputs(name):
     torch.cuda.synchronize()
     logits = model.last_logits(B).float().cpu()
     top2 = o_logits.topk(2, dim=-1).values
+    # other images, same configuration: the fixture's ref16 errors are the yard-stick of that configuration
     _check_against(o_logits, o_loss, o_grads, top2[:, 0] - top2[:, 1], logits, loss_rows.cpu(), pred.cpu(),
-                   {k: v.cpu() for k, v in grads.items()})
+                   {k: v.cpu() for k, v in grads.items()}, ref16=_ref16_errors(fx))
 
 
 @pytest.mark.parametrize("name", ["tiny_coop_end", "tiny_vpt_deep", "tiny_upt_identity"])
@@ -110,12 +142,12 @@ def test_encoders_match_golden_features():
     from tests.helpers import build_custom_clip, rel_err
     model, fx, case, sd, image, pp, upt = build_custom_clip("tiny_vpt_deep", "fp32")
     f = model.image_encoder(image.cuda())
-    assert rel_err(f.float().cpu(), fx["image_features"]) < 3e-3
+    assert rel_err(f.float().cpu(), fx["image_features"]) < 5e-4
     model, fx, case, sd, image, pp, upt = build_custom_clip("tiny_coop_middle_cut", "fp32")
     prompts = model.prompt_learner.forward_coop()
     assert rel_err(prompts.float().cpu(), fx["prompts"]) < 1e-3
     t = model.text_encoder(prompts, model.tokenized_prompts)
-    assert rel_err(t.float().cpu(), fx["text_features"]) < 3e-3
+    assert rel_err(t.float().cpu(), fx["text_features"]) < 1e-3
 
 
 def test_full_size_properties():
@@ -177,9 +209,9 @@ def test_causal_cut_of_the_text_tower_changes_nothing(name, monkeypatch):
     torch.cuda.synchronize()
     # (two equally valid fp16 evaluations: they differ by what each differs from the fp32 reference, measured 4e-3 on the
     # ViT-B/16 context gradient)
-    assert rel_err(model.last_logits(image.shape[0]).float(), out["1"][0]) < LOGIT_TOL
+    assert rel_err(model.last_logits(image.shape[0]).float(), out["1"][0]) < LOGIT_CAP
     for k in out["1"][1]:
-        assert rel_err(grads[k].float(), out["1"][1][k]) < GRAD_TOL / 2, k
+        assert rel_err(grads[k].float(), out["1"][1][k]) < 1e-2, k
 
 
 @pytest.mark.parametrize("prec", ["fp32", "fp16"])
@@ -216,8 +248,10 @@ def test_vpt_dropout_training_step_matches_oracle_on_the_kernels_masks(name, pre
     kw["drop_keep"] = keep
     o_logits, o_loss, o_grads = O.train_step(image, fx["label"], sd, pp, **kw)
     top2 = o_logits.topk(2, dim=-1).values
+    base = name.replace("_dropout", "") if name != "tiny_vpt_shallow_project_dropout" else "tiny_vpt_shallow_project_coop"
+    from tests.conftest import load_golden
     _check_against(o_logits, o_loss, o_grads, top2[:, 0] - top2[:, 1], logits, loss_rows.cpu(), pred.cpu(),
-                   {k: g.cpu() for k, g in grads.items()})
+                   {k: g.cpu() for k, g in grads.items()}, ref16=(_ref16_errors(load_golden(base))[0], {}))
     # another seed: another mask, other logits; eval mode: no dropout at all (nn.Dropout semantics)
     pl.drop_seed_override = 7
     model.loss_and_grads(img, fx["label"].cuda(), fx["task"])
@@ -226,4 +260,4 @@ def test_vpt_dropout_training_step_matches_oracle_on_the_kernels_masks(name, pre
     kw["drop_p"], kw["drop_keep"] = 0.0, None
     e_logits, _, _ = O.train_step(image, fx["label"], sd, pp, **kw)
     model.loss_and_grads(img, fx["label"].cuda(), fx["task"])
-    assert rel_err(model.last_logits(B).float().cpu(), e_logits) <= LOGIT_TOL
+    assert rel_err(model.last_logits(B).float().cpu(), e_logits) <= LOGIT_CAP

@@ -59,10 +59,13 @@ def test_checkpoint_roundtrip_and_reference_key_names(tmp_path):
     tr, fx, case, sd, image, pp, upt = _trainer("tiny_upt_identity")
     sdict = tr.model.prompt_learner.state_dict()
     assert {"ctx", "vpt_embeddings", "vpt_embeddings_deep", "token_prefix", "token_suffix"} <= set(sdict)
-    tr.save_model(3, str(tmp_path), is_best=True)
+    tr.save_model(3, str(tmp_path), is_best=True)  # Dassl's layout: 0-based epoch 3 -> model.pth.tar-4, epoch field 4
+    ck = torch.load(tmp_path / "prompt_learner" / "model.pth.tar-4", weights_only=False)
+    assert ck["epoch"] == 4 and {"state_dict", "optimizer", "scheduler", "val_result"} <= set(ck)
+    assert (tmp_path / "prompt_learner" / "checkpoint").read_text().strip() == "model.pth.tar-4"
     with torch.no_grad():
         tr.model.prompt_learner.ctx.zero_()
-    tr.load_model(str(tmp_path), epoch=3)
+    tr.load_model(str(tmp_path), epoch=4)
     assert torch.equal(tr.model.prompt_learner.ctx.detach().cpu().float(), pp["ctx"])
     tr.load_model(str(tmp_path))  # model-best.pth.tar
 
@@ -198,3 +201,44 @@ def test_fp32_eval_outputs_do_not_alias_the_engine_buffer():
     res = tr.test()
     want = 100.0 * float((torch.cat([oa, ob]).argmax(1).cpu() == torch.cat([labs, labs])).float().mean())
     assert abs(res - want) < 1e-6
+
+
+def test_cli_trains_resumes_and_evaluates(tmp_path, capsys):
+    """python -m mvlpt_b200.train (the reference's train.py flags, train.py:171-295) on the reference-shaped config keys
+    with the synthetic stand-ins: 2 epochs with per-epoch validation (TEST.FINAL_MODEL best_val) -> checkpoints in Dassl's
+    layout; --resume continues at epoch 2 and ends bit-identical to an uninterrupted 3-epoch run; --eval-only
+    --model-dir --load-epoch reproduces the final test result."""
+    from mvlpt_b200 import train as T
+
+    def run(*argv):
+        return T.main(T.build_parser().parse_args(list(argv)))
+
+    common = ["--trainer", "MVLPT", "--synthetic", "--synthetic-classes", "6", "--synthetic-batches", "3", "--seed", "1",
+              "--backbone", "tiny", "--dataset-coop",
+              "TRAINER.MVLPT.VPT.N_CTX", "4", "TRAINER.MVLPT.COOP.N_CTX", "4", "TRAINER.MVLPT.PROJECT_METHOD", "identity",
+              "TRAINER.MVLPT.COOP.CLASS_TOKEN_POSITION", "end", "INPUT.SIZE", "(64, 64)",
+              "DATALOADER.TRAIN_X.BATCH_SIZE", "4", "DATALOADER.TEST.BATCH_SIZE", "5", "OPTIM.LR", "0.05",
+              "OPTIM.WARMUP_EPOCH", "0", "TEST.FINAL_MODEL", "best_val"]
+    a, b = str(tmp_path / "a"), str(tmp_path / "b")
+    full = run(*common, "--output-dir", a, "OPTIM.MAX_EPOCH", "3")
+    assert (tmp_path / "a" / "prompt_learner" / "model.pth.tar-3").exists()
+    assert (tmp_path / "a" / "prompt_learner" / "model-best.pth.tar").exists()
+    assert isinstance(full.final_result, float)
+    # the schedule is a function of MAX_EPOCH: interrupt the same 3-epoch schedule after 2 epochs by checkpoint frequency
+    part = run(*common, "--output-dir", b, "OPTIM.MAX_EPOCH", "3", "TRAIN.CHECKPOINT_FREQ", "1", "TEST.NO_TEST", "True")
+    import os
+    os.remove(tmp_path / "b" / "prompt_learner" / "model.pth.tar-3")
+    (tmp_path / "b" / "prompt_learner" / "checkpoint").write_text("model.pth.tar-2\n")
+    res = run(*common, "--output-dir", b, "--resume", b, "OPTIM.MAX_EPOCH", "3", "TEST.NO_TEST", "True")
+    assert res.start_epoch == 2
+    out = capsys.readouterr().out
+    assert "Previous epoch: 2" in out
+    ck_a = torch.load(tmp_path / "a" / "prompt_learner" / "model.pth.tar-3", weights_only=False)
+    ck_b = torch.load(tmp_path / "b" / "prompt_learner" / "model.pth.tar-3", weights_only=False)
+    for k, v in ck_a["state_dict"].items():
+        assert torch.equal(v, ck_b["state_dict"][k]), k
+    ev = run(*common, "--eval-only", "--model-dir", a, "--load-epoch", "3")
+    with torch.no_grad():
+        want = ev.test()
+    last = run(*common, "--output-dir", str(tmp_path / "c"), "OPTIM.MAX_EPOCH", "3", "TEST.FINAL_MODEL", "last_step")
+    assert abs(last.final_result - want) < 1e-6

@@ -82,6 +82,31 @@ if "gemm" in what:
               f"{2.0 * M * N * K / t / 1e6:7.1f} TF/s", flush=True)
         del A, out, r, ai, ao
 
+if "lnfuse" in what:
+    import os
+    for (M, N, K) in [(52480, 768, 768), (52480, 768, 3072), (50432, 768, 768), (50432, 768, 3072), (25000, 512, 512),
+                      (25000, 512, 2048), (2500, 512, 512), (2500, 512, 2048)]:
+        nb = 3
+        A = [(torch.randn(M, K, device=dev) * 0.5).half() for _ in range(nb)]
+        W = (torch.randn(N, K, device=dev) * 0.05).half()
+        b = (torch.randn(N, device=dev) * 0.1).half()
+        out = [torch.empty(M, N, device=dev) for _ in range(nb)]
+        r = [torch.randn(M, N, device=dev) for _ in range(nb)]
+        h = [torch.empty(M, N, device=dev, dtype=torch.half) for _ in range(nb)]
+        g = torch.ones(N, device=dev)
+        bb = torch.zeros(N, device=dev)
+        res = {}
+        t = timeit(lambda i: ops.gemm(A[i % nb], W, out[i % nb], bias=b, resid=r[i % nb]))
+        t_ln = timeit(lambda i: ops.ln_fwd(out[i % nb], g, bb, h[i % nb], M, N))
+        res["plain"], res["ln_kernel"] = t, t_ln
+        for dbg in ("0", "1", "2", "3"):
+            os.environ["MVLPT_LN_DBG"] = dbg
+            res["fused_dbg" + dbg] = timeit(lambda i: ops.gemm(A[i % nb], W, out[i % nb], bias=b, resid=r[i % nb],
+                                                               ln=(g, bb, h[i % nb])))
+        os.environ["MVLPT_LN_DBG"] = "0"
+        print(f"lnfuse M={M} N={N} K={K}: " + "  ".join(f"{k} {v:7.1f}" for k, v in res.items()), flush=True)
+        del A, out, r, h
+
 if "ln" in what:
     for (M, d) in [(52480, 768), (7700, 512)]:
         nb = 3
