@@ -61,16 +61,34 @@ typedef struct {
 
 int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* aux_in,
                void* aux_out, const void* resid, void* out, mvlpt_stream_t stream);
-/* The residual-stream linears with the FOLLOWING LayerNorm fused in (clip/model.py:185-188: `x + attn(ln_1(x))` feeds
- * ln_2, `x + mlp(ln_2(x))` feeds the next block's ln_1; LayerNorm itself clip/model.py:153-159):
- *   out[M,N] fp32 = A.W^T + bias + resid        and        ln_out[M,N] fp16 = LN(out) * ln_gamma + ln_beta
- * in ONE kernel: a CTA pair owns whole 256-row blocks, accumulates the row sums in the epilogue that already holds the
- * fp32 row, and normalises the block out of L2 once its last column tile is stored — no LayerNorm kernel re-reads the
- * stream from HBM.  Needs out_f32, act 0, N == the row width with N % 256 == 0, N <= 1024, M >= 256
- * (mvlpt_gemm_ln_supported); ln_gamma/ln_beta fp32 [N]; ln_out row stride N. */
-int mvlpt_gemm_ln_supported(int M, int N);
-int mvlpt_gemm_ln(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* resid, void* out,
-                  const void* ln_gamma, const void* ln_beta, void* ln_out, float ln_eps, mvlpt_stream_t stream);
+/* LayerNorm carried through the linears instead of run as a kernel (clip/model.py:185-188: `x + attn(ln_1(x))` feeds
+ * ln_2, `x + mlp(ln_2(x))` feeds the next block's ln_1; LayerNorm itself clip/model.py:153-159).  With mean mu and
+ * rstd of a row x:   LN(x).W^T + b = rstd * ( xt.W^T - (mu - c) * sg ) + bp,   xt[k] = (x[k] - c) * gamma[k] (fp16),
+ * sg[n] = sum_k gamma[k] W[n,k],  bp[n] = b[n] + sum_k beta[k] W[n,k]  (fp32, precomputed per layer),  any centring c.
+ *   producer side (rec_out != NULL): the residual-stream linear (out_f32, N == width) additionally writes xt of its
+ *     output rows straight from the epilogue registers, centred on the mean of its residual rows (from rec_in; c = 0 when
+ *     rec_in is NULL), and the partial sums of (x - c), (x - c)^2 into the row records rec_out;
+ *   consumer side (rec != NULL): A is the xt of the rows to normalise (K == width); mean / rstd are finished from the
+ *     records and the identity above is applied in the epilogue (then act / aux_out as in mvlpt_gemm); `bias` is bp
+ *     (fp16 [N]) and `sg` fp16 [N].
+ * Row record: MVLPT_LN_REC floats = 8 (sum, sum of squares) pairs of 128-column slices, the centring value at index 16.
+ * Needs the CTA-pair kernel: M >= 256, N % 256 == 0, width % 256 == 0, width <= 1024 (mvlpt_gemm_ln_supported).
+ * mvlpt_ln_prep starts the chain from a plain fp32 row block: xt = (x - mean) * gamma, record = (0, M2 | c = mean). */
+#define MVLPT_LN_REC 20
+typedef struct {
+    const void* rec_in; /* producer: fp32 [M, MVLPT_LN_REC] records of the residual rows, or NULL */
+    void* rec_out;      /* producer: fp32 [M, MVLPT_LN_REC] records of the output rows           */
+    const void* gamma;  /* producer: fp32 [width] gamma of the LayerNorm that will consume `out`  */
+    void* xt;           /* producer: fp16 [M, width]                                              */
+    const void* rec;    /* consumer: fp32 [M, MVLPT_LN_REC] records of the A rows                 */
+    const void* sg;     /* consumer: fp16 [N] (the folded bias bp goes in as `bias`)              */
+    int width;          /* row width d of the normalised rows                                     */
+    float eps;
+} mvlpt_ln_carry;
+int mvlpt_gemm_ln_supported(int M, int width);
+int mvlpt_gemm_ln(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* aux_in,
+                  void* aux_out, const void* resid, void* out, const mvlpt_ln_carry* ln, mvlpt_stream_t stream);
+int mvlpt_ln_prep(const void* x, const void* gamma, void* xt, void* rec, int rows, int d, mvlpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Attention core, head width 64 (d == heads*64), L <= 288, packed qkv [N*L, 3d] fp16 (Q | K | V).
@@ -133,11 +151,11 @@ int mvlpt_embed_assemble(const void* pe, const void* cls, const void* pos, const
                          mvlpt_stream_t stream);
 int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
                           uint64_t seed, int slab, mvlpt_stream_t stream);
-/* Same, and h[b,1+j] = LN(x[b,1+j]) * gamma + beta (fp16 [B*L, d]) for the rows just written: the block's ln_1 output,
- * when the previous block's mvlpt_gemm_ln already produced it for all rows (h NULL = plain mvlpt_set_prompt_rows). */
+/* Same, and for the rows just written xt[b,1+j] = (x - mean) * gamma (fp16 [B*L, d]) and their row records
+ * (mvlpt_gemm_ln): the previous block's FC2 produced xt / records for the rows this call replaces.  xt NULL = plain
+ * mvlpt_set_prompt_rows. */
 int mvlpt_set_prompt_rows_ln(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
-                             uint64_t seed, int slab, void* h, const void* gamma, const void* beta, float eps,
-                             mvlpt_stream_t stream);
+                             uint64_t seed, int slab, void* xt, void* rec, const void* gamma, mvlpt_stream_t stream);
 int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int d, float inv_scale, int zero_rows,
                       float drop_p, uint64_t seed, int slab, mvlpt_stream_t stream);
 int mvlpt_dropout_keep(void* keep, int B, int v, int d, float drop_p, uint64_t seed, int slab, mvlpt_stream_t stream);

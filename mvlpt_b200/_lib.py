@@ -23,6 +23,14 @@ class GemmDesc(Structure):
                 ("act", c_int), ("out_f32", c_int), ("alpha", c_float)]
 
 
+class LnCarry(Structure):
+    """mvlpt_ln_carry of include/mvlpt_sm100.h."""
+    _fields_ = [("rec_in", c_void_p), ("rec_out", c_void_p), ("gamma", c_void_p), ("xt", c_void_p),
+                ("rec", c_void_p), ("sg", c_void_p), ("width", c_int), ("eps", c_float)]
+
+
+LN_REC = 20  # MVLPT_LN_REC
+
 _lib = None
 
 

@@ -103,14 +103,13 @@ static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* 
         forced = e ? atoi(e) : 0;
     }
     if (forced >= 2 && forced <= kGemmMaxStages2) stages = forced;
-    int slabs = (kGemmSmemBudget + 1024 - (ep.ln_out ? 2048 : 0) - stages * kStage) / kGemmSlab;
+    int slabs = (kGemmSmemBudget + 1024 - stages * kStage) / kGemmSlab;
     int ring = slabs / per;
     if (ring > kGemmMaxRing) ring = kGemmMaxRing;
     if (ring < 2) return fail(MVLPT_ESHAPE, "mvlpt_gemm: no room for the output ring");
     ep.stages = stages;
     ep.ring = ring;
-    // 256 B of barriers + TMEM slot, then 2 KB of per-row LayerNorm statistics (fused-LN epilogue)
-    const int smem_bytes = stages * kStage + ring * per * kGemmSlab + 256 + (ep.ln_out ? 2048 : 0);
+    const int smem_bytes = stages * kStage + ring * per * kGemmSlab + 256;
     CUtensorMap ta, tw, to, tx, ti;
     {
         uint64_t dims[2] = {(uint64_t)d->K, (uint64_t)d->M};
@@ -151,8 +150,7 @@ static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* 
     }
     static DynSmemCache attr;
     if (int rc = ensure_dyn_smem(gemm_f16_tn_2sm_kernel<F32>, (size_t)smem_bytes, attr)) return rc;
-    // with the fused LayerNorm a pair owns whole 256-row blocks (all column tiles of a block back to back)
-    const int tiles = ep.ln_out ? cdiv(d->M, 2 * kGemmBM) : cdiv(d->M, 2 * kGemmBM) * cdiv(d->N, 256);
+    const int tiles = cdiv(d->M, 2 * kGemmBM) * cdiv(d->N, 256);
     const int pairs = tiles < sm_count() / 2 ? tiles : sm_count() / 2;
     MVLPT_CUDA_OK(launch_pdl(gemm_f16_tn_2sm_kernel<F32>, dim3(2 * pairs), dim3(kGemm2Threads), smem_bytes, stream, 2, ta, tw, to,
                              tx, ti, d->M, d->N, d->K, ep));
@@ -160,37 +158,47 @@ static int launch_gemm_2sm(const mvlpt_gemm_desc* d, const void* A, const void* 
 }
 
 static int gemm_impl(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* aux_in,
-                     void* aux_out, const void* resid, void* out, const void* ln_gamma, const void* ln_beta, void* ln_out,
-                     float ln_eps, mvlpt_stream_t stream);
+                     void* aux_out, const void* resid, void* out, const mvlpt_ln_carry* ln, mvlpt_stream_t stream);
 
 extern "C" int mvlpt_gemm(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias,
                           const void* aux_in, void* aux_out, const void* resid, void* out, mvlpt_stream_t stream) {
-    return gemm_impl(d, A, W, bias, aux_in, aux_out, resid, out, nullptr, nullptr, nullptr, 0.f, stream);
+    return gemm_impl(d, A, W, bias, aux_in, aux_out, resid, out, nullptr, stream);
 }
 
-extern "C" int mvlpt_gemm_ln_supported(int M, int N) {
+extern "C" int mvlpt_gemm_ln_supported(int M, int width) {
     static int off = -1;
     if (off < 0) off = (getenv("MVLPT_GEMM_1SM") || getenv("MVLPT_NO_FUSED_LN")) ? 1 : 0;
-    return !off && M >= 256 && N >= 256 && (N % 256) == 0 && N <= 1024;
+    return !off && M >= 256 && width >= 256 && (width % 256) == 0 && width <= 1024;
 }
 
-extern "C" int mvlpt_gemm_ln(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* resid,
-                             void* out, const void* ln_gamma, const void* ln_beta, void* ln_out, float ln_eps,
+extern "C" int mvlpt_gemm_ln(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias,
+                             const void* aux_in, void* aux_out, const void* resid, void* out, const mvlpt_ln_carry* ln,
                              mvlpt_stream_t stream) {
-    if (!d || !ln_gamma || !ln_beta || !ln_out) return fail(MVLPT_EINVAL, "mvlpt_gemm_ln: null argument");
-    if (!d->out_f32 || d->act != ACT_NONE) return fail(MVLPT_ESHAPE, "mvlpt_gemm_ln: fp32 output without activation only");
-    if (!mvlpt_gemm_ln_supported(d->M, d->N))
-        return fail(MVLPT_ESHAPE, "mvlpt_gemm_ln: needs M >= 256 and N a multiple of 256 up to 1024 (got M=%d N=%d)", d->M,
-                    d->N);
-    if ((reinterpret_cast<uintptr_t>(ln_gamma) & 15) || (reinterpret_cast<uintptr_t>(ln_beta) & 15) ||
-        (reinterpret_cast<uintptr_t>(ln_out) & 15))
-        return fail(MVLPT_EINVAL, "mvlpt_gemm_ln: gamma/beta/ln_out must be 16-byte aligned");
-    return gemm_impl(d, A, W, bias, nullptr, nullptr, resid, out, ln_gamma, ln_beta, ln_out, ln_eps, stream);
+    if (!d || !ln) return fail(MVLPT_EINVAL, "mvlpt_gemm_ln: null argument");
+    const bool prod = ln->rec_out != nullptr, cons = ln->rec != nullptr;
+    if (prod == cons) return fail(MVLPT_EINVAL, "mvlpt_gemm_ln: exactly one of the producer (rec_out) / consumer (rec) sides");
+    if (!mvlpt_gemm_ln_supported(d->M, ln->width) || (d->N % 256))
+        return fail(MVLPT_ESHAPE, "mvlpt_gemm_ln: needs M >= 256, N %% 256 == 0 and a row width that is a multiple of 256 up "
+                                  "to 1024 (got M=%d N=%d width=%d)", d->M, d->N, ln->width);
+    if (prod) {
+        if (!d->out_f32 || d->act != ACT_NONE || d->N != ln->width || d->alpha != 1.f)
+            return fail(MVLPT_ESHAPE, "mvlpt_gemm_ln producer: fp32 output of the row width, no activation, alpha 1");
+        if (!ln->gamma || !ln->xt) return fail(MVLPT_EINVAL, "mvlpt_gemm_ln producer: gamma and xt are required");
+        if ((reinterpret_cast<uintptr_t>(ln->gamma) | reinterpret_cast<uintptr_t>(ln->xt) |
+             reinterpret_cast<uintptr_t>(ln->rec_out) | reinterpret_cast<uintptr_t>(ln->rec_in)) & 15)
+            return fail(MVLPT_EINVAL, "mvlpt_gemm_ln: gamma / xt / records must be 16-byte aligned");
+    } else {
+        if (d->out_f32 || d->K != ln->width || d->alpha != 1.f || !bias)
+            return fail(MVLPT_ESHAPE, "mvlpt_gemm_ln consumer: fp16 output, K == row width, alpha 1, bias = bp");
+        if (!ln->sg) return fail(MVLPT_EINVAL, "mvlpt_gemm_ln consumer: sg is required");
+        if ((reinterpret_cast<uintptr_t>(ln->sg) | reinterpret_cast<uintptr_t>(ln->rec)) & 15)
+            return fail(MVLPT_EINVAL, "mvlpt_gemm_ln: sg / records must be 16-byte aligned");
+    }
+    return gemm_impl(d, A, W, bias, aux_in, aux_out, resid, out, ln, stream);
 }
 
 static int gemm_impl(const mvlpt_gemm_desc* d, const void* A, const void* W, const void* bias, const void* aux_in,
-                     void* aux_out, const void* resid, void* out, const void* ln_gamma, const void* ln_beta, void* ln_out,
-                     float ln_eps, mvlpt_stream_t stream) {
+                     void* aux_out, const void* resid, void* out, const mvlpt_ln_carry* ln, mvlpt_stream_t stream) {
     if (!d || !A || !W || !out) return fail(MVLPT_EINVAL, "mvlpt_gemm: null argument");
     if (d->M <= 0 || d->N <= 0 || d->K <= 0) return fail(MVLPT_EINVAL, "mvlpt_gemm: M,N,K must be positive");
     if (d->lda < d->K || d->ldw < d->K || d->ld_out < d->N)
@@ -221,16 +229,22 @@ static int gemm_impl(const mvlpt_gemm_desc* d, const void* A, const void* W, con
     ep.act = d->act;
     ep.alpha = d->alpha;
     ep.stages = ep.ring = 0;
-    ep.ln_gamma = static_cast<const float*>(ln_gamma);
-    ep.ln_beta = static_cast<const float*>(ln_beta);
-    ep.ln_out = static_cast<__half*>(ln_out);
-    ep.ln_x = static_cast<const float*>(out);
-    ep.ln_ldx = d->ld_out;
-    ep.ln_eps = ln_eps;
-    ep.ln_dbg = 0;
-    if (ln_out) {
-        const char* e = getenv("MVLPT_LN_DBG");  // tuning only: the result is wrong with any bit set
-        ep.ln_dbg = e ? atoi(e) : 0;
+    ep.lnp_rec_in = ep.lnp_gamma = ep.lnc_rec = nullptr;
+    ep.lnc_sg = nullptr;
+    ep.lnp_rec_out = nullptr;
+    ep.lnp_xt = nullptr;
+    ep.ln_parts = 0;
+    ep.ln_inv_d = ep.ln_eps = 0.f;
+    if (ln) {
+        ep.lnp_rec_in = static_cast<const float*>(ln->rec_in);
+        ep.lnp_rec_out = static_cast<float*>(ln->rec_out);
+        ep.lnp_gamma = static_cast<const float*>(ln->gamma);
+        ep.lnp_xt = static_cast<__half*>(ln->xt);
+        ep.lnc_rec = static_cast<const float*>(ln->rec);
+        ep.lnc_sg = static_cast<const __half*>(ln->sg);
+        ep.ln_parts = ln->width / 128;
+        ep.ln_inv_d = 1.f / (float)ln->width;
+        ep.ln_eps = ln->eps;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (use_2sm(d))

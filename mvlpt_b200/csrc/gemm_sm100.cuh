@@ -37,17 +37,26 @@ struct GemmEpilogue {
     float alpha;
     int stages;          // depth of the operand ring
     int ring;            // output ring slots (each 1 slab, or 2 when has_aux_out)
-    // Fused LayerNorm of the OUTPUT rows (CTA-pair kernel, fp32 output, N == the row width): the residual-stream GEMMs
-    // (out-proj, FC2) also emit h = LN(out) * gamma + beta as fp16, i.e. the ln_2 / next block's ln_1 of
-    // clip/model.py:186-187, so no separate LayerNorm kernel reads the stream back from HBM.
-    const float* ln_gamma;  // [N] or nullptr (no fusion)
-    const float* ln_beta;   // [N]
-    __half* ln_out;         // [M, N] fp16, row stride N
-    const float* ln_x;      // the fp32 output buffer itself (read back from L2 once its row block is complete)
-    int ln_ldx;             // its row stride in elements
+    // ---- LayerNorm carried THROUGH the linears (CTA-pair kernel only; see the comment above gemm_f16_tn_2sm_kernel) ----
+    // producer side (fp32 residual-stream output, N == row width): also emits xt = (out - c) * gamma as fp16 and the
+    // row record of `out`
+    const float* lnp_rec_in;   // records of the residual input rows (their mean becomes the centring value c) or nullptr
+    float* lnp_rec_out;        // records of the output rows
+    const float* lnp_gamma;    // [N] gamma of the LayerNorm that will consume `out`
+    __half* lnp_xt;            // [M, N] fp16, row stride N
+    // consumer side (A operand = xt of the rows to normalise): out = rstd * (acc - delta * sg) + bp, bp passed as `bias`
+    const float* lnc_rec;      // records of the A rows, or nullptr
+    const __half* lnc_sg;      // [N] fp16: sum_k gamma[k] W[n,k]   (bias = bp[n] = b[n] + sum_k beta[k] W[n,k])
+    int ln_parts;              // partial (sum, sum of squares) pairs per record = 2 * (row width / 256)
+    float ln_inv_d;            // 1 / row width
     float ln_eps;
-    int ln_dbg;             // tuning only (MVLPT_LN_DBG): 1 skip the normalisation pass, 2 skip the store-completion wait
 };
+
+// Row record of a residual-stream row x[0..d): kLnRec floats = up to 8 pairs (S1_j, S2_j) — sums of (x - c) and
+// (x - c)^2 over the j-th 128-column slice, written by the epilogue thread that produced the slice — then the centring
+// value c at index 16.  mean = c + sum S1 / d, var = sum S2 / d - (sum S1 / d)^2.
+constexpr int kLnRec = 20;
+constexpr int kLnRecC = 16;
 
 constexpr int kGemmBM = 128;
 constexpr int kGemmBK = 64;
@@ -368,6 +377,16 @@ gemm_f16_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_cons
 // The even CTA issues the MMAs; TMA loads of both CTAs count on its `full` barrier; tcgen05.commit multicasts to the
 // `empty` / `tfull` barriers of both; the epilogue warps of both CTAs arrive on its `tempty` barrier.
 // The epilogue is the one of the kernel above, per CTA on its own 128 accumulator rows, with twice the warps.
+//
+// LayerNorm without a LayerNorm kernel (clip/model.py:153-159 as used at :186-187).  For a row x with mean mu and
+// rstd = (var + eps)^-1/2:   LN(x) . W^T + b  =  rstd * ( xt . W^T  -  (mu - c) * sg )  +  bp      with
+//   xt[k] = (x[k] - c) * gamma[k]  (fp16),   sg[n] = sum_k gamma[k] W[n,k],   bp[n] = b[n] + sum_k beta[k] W[n,k],
+// for ANY centring value c.  The residual-stream GEMM that produces x (out-proj, FC2) takes c = the mean of its residual
+// input (known from that row's record; the block's update moves the mean only a little, so xt is centred to fp16
+// accuracy and mu - c is small), writes xt straight from the registers that hold the fp32 row, and leaves the partial
+// sums of (x - c), (x - c)^2 of its 128-column slice in the row record.  The GEMM that consumes LN(x) (QKV, FC1) reads xt
+// as its A operand, finishes mean / rstd from the record and applies the identity above in its epilogue.  The rounding is
+// that of the explicit LayerNorm path — one fp16 rounding of a centred, gamma-scaled row — the weights are untouched.
 template <bool OUT_F32>
 __global__ void __launch_bounds__(kGemm2Threads, 1)
 gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_w,
@@ -402,22 +421,6 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
     const int n_tiles = (N + BN - 1) / BN;
     const int num_tiles = m_tiles * n_tiles;
     const int k_blocks = (K + kGemmBK - 1) / kGemmBK;
-    // Tile schedule of this pair.  Default: tiles pair, pair + num_pairs, ... of the row-major (m, n) tile grid.  With the
-    // fused LayerNorm a pair owns whole 256-row blocks — all n_tiles column tiles of a block back to back — so that the
-    // epilogue sees complete rows and can finish their statistics.
-    const bool by_rows = OUT_F32 && ep.ln_out != nullptr;
-    const int my_tiles = by_rows ? (pair < m_tiles ? ((m_tiles - 1 - pair) / num_pairs + 1) * n_tiles : 0)
-                                 : (pair < num_tiles ? (num_tiles - 1 - pair) / num_pairs + 1 : 0);
-    auto tile_of = [&](int it, int& mt, int& nt) {
-        if (by_rows) {
-            mt = pair + (it / n_tiles) * num_pairs;
-            nt = it % n_tiles;
-        } else {
-            const int t = pair + it * num_pairs;
-            mt = t / n_tiles;
-            nt = t % n_tiles;
-        }
-    };
 
     if (warp == 0 && lane == 0) {
         if (smem_u32(smem) & 1023u) {
@@ -456,11 +459,9 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         if (lane == 0) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int it = 0; it < my_tiles; ++it) {
-                int mt, nt;
-                tile_of(it, mt, nt);
-                const int m0 = mt * (2 * kGemmBM) + (int)rank * kGemmBM;
-                const int n0 = nt * BN + (int)rank * (BN / 2);
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+                const int m0 = (tile / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM;
+                const int n0 = (tile % n_tiles) * BN + (int)rank * (BN / 2);
                 for (int kb = 0; kb < k_blocks; ++kb) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);  // both CTAs' bytes
@@ -481,7 +482,7 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
             uint32_t phase = 0;
             int acc = 0;
             uint32_t acc_phase = 0;
-            for (int it = 0; it < my_tiles; ++it) {
+            for (int tile = pair; tile < num_tiles; tile += num_pairs) {
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
@@ -522,28 +523,47 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
         int acc = 0;
         uint32_t acc_phase = 0;
         int g = 0;  // steps done by this CTA
+        const int my_tiles = pair < num_tiles ? (num_tiles - 1 - pair) / num_pairs + 1 : 0;
         const int total_steps = my_tiles * kSteps;
         // TMA load of the epilogue input of step gg into its ring slot (issuer thread only)
         auto issue_in = [&](int gg) {
             if (gg >= total_steps) return;
-            int mt, nt;
-            tile_of(gg / kSteps, mt, nt);
-            const int mm = mt * (2 * kGemmBM) + (int)rank * kGemmBM, nn = nt * BN + (gg % kSteps) * SW;
+            const int t = pair + (gg / kSteps) * num_pairs;
+            const int mm = (t / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM, nn = (t % n_tiles) * BN + (gg % kSteps) * SW;
             const int slot = gg % R;
             mbar_arrive_expect_tx(&in_full[slot], kGemmSlab);
             tma_load_2d(smem_e + slot * kGemmSlab, &tmap_in, &in_full[slot], nn, mm);
         };
         if (has_in && issuer)
             for (int gg = 0; gg < R - 1; ++gg) issue_in(gg);
-        // fused LayerNorm: running sum / sum of squares of this thread's half of its output row
-        float ln_s1 = 0.f, ln_s2 = 0.f;
-        float2* ln_stats = reinterpret_cast<float2*>(tmem_slot + 4);  // [128 rows][2 column halves], 2 KB behind the barriers
 
-        for (int it = 0; it < my_tiles; ++it) {
-            int mt, nt;
-            tile_of(it, mt, nt);
-            const int m0 = mt * (2 * kGemmBM) + (int)rank * kGemmBM;
-            const int n0 = nt * BN;
+        const bool lnc = !OUT_F32 && ep.lnc_rec != nullptr;
+        const bool lnp = OUT_F32 && ep.lnp_rec_out != nullptr;
+        for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+            const int m0 = (tile / n_tiles) * (2 * kGemmBM) + (int)rank * kGemmBM;
+            const int n0 = (tile % n_tiles) * BN;
+            // LayerNorm carried through the linears: per-row coefficients out of the row record (loads overlap the wait)
+            const int gm = m0 + r;              // global row of this thread
+            float ln_a = 1.f, ln_d = 0.f;       // consumer: out = ln_a * acc + ln_d * sg + bp
+            float ln_c = 0.f, ln_s1 = 0.f, ln_s2 = 0.f;  // producer: centring value, partial sums of this thread's slice
+            if ((lnc || (lnp && ep.lnp_rec_in)) && gm < M) {
+                const float* rec = (lnc ? ep.lnc_rec : ep.lnp_rec_in) + (size_t)gm * kLnRec;
+                float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (2 * q < ep.ln_parts) {
+                        const float4 t = __ldg(reinterpret_cast<const float4*>(rec) + q);
+                        s1 += t.x + t.z;
+                        s2 += t.y + t.w;
+                    }
+                const float delta = s1 * ep.ln_inv_d;  // mean - c
+                if (lnc) {
+                    ln_a = rsqrtf(fmaxf(s2 * ep.ln_inv_d - delta * delta, 0.f) + ep.ln_eps);
+                    ln_d = -delta * ln_a;
+                } else {
+                    ln_c = __ldg(rec + kLnRecC) + delta;  // the mean of the residual input row
+                }
+            }
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             const uint32_t t_row = tmem_base + (uint32_t(quarter * 32) << 16) + acc * BN + half * HC;
@@ -559,6 +579,11 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 if (bias_vec) {
 #pragma unroll
                     for (int q = 0; q < HC / 8; ++q) braw[q] = __ldg(reinterpret_cast<const uint4*>(ep.bias + c0) + q);
+                }
+                uint4 sgraw[HC / 8];
+                if (lnc) {
+#pragma unroll
+                    for (int q = 0; q < HC / 8; ++q) sgraw[q] = __ldg(reinterpret_cast<const uint4*>(ep.lnc_sg + c0) + q);
                 }
                 if (has_in) {
                     mbar_wait(&in_full[slot], (uint32_t)(g / R) & 1);  // input landed (implies the slot was drained)
@@ -585,7 +610,22 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                     for (int j = 0; j < HC; ++j) v[j] *= ep.alpha;
                 }
-                if (bias_vec) {
+                if (lnc) {
+                    // out = rstd * acc + (-(mean - c) * rstd * sg + bp): the bracket in half2 (a small correction plus the
+                    // folded bias), N % 256 == 0 in this mode so bias_vec holds
+                    const __half2 d2 = __float2half2_rn(ln_d);
+#pragma unroll
+                    for (int q = 0; q < HC / 8; ++q) {
+                        const __half2* sg2 = reinterpret_cast<const __half2*>(&sgraw[q]);
+                        const __half2* bp2 = reinterpret_cast<const __half2*>(&braw[q]);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float2 f = __half22float2(__hfma2(d2, sg2[j], bp2[j]));
+                            v[q * 8 + 2 * j] = fmaf(v[q * 8 + 2 * j], ln_a, f.x);
+                            v[q * 8 + 2 * j + 1] = fmaf(v[q * 8 + 2 * j + 1], ln_a, f.y);
+                        }
+                    }
+                } else if (bias_vec) {
 #pragma unroll
                     for (int q = 0; q < HC / 8; ++q) {
                         const __half2* h2 = reinterpret_cast<const __half2*>(&braw[q]);
@@ -617,12 +657,25 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                         *dst = make_uint4(__float_as_uint(v[4 * u]), __float_as_uint(v[4 * u + 1]),
                                           __float_as_uint(v[4 * u + 2]), __float_as_uint(v[4 * u + 3]));
                     }
-                    if (by_rows) {
+                    if (lnp && gm < M) {
+                        // xt = (x - c) * gamma for this thread's 16 columns, straight from the registers: 32 contiguous
+                        // bytes of its row; partial sums of the centred values for the row record
+                        uint32_t xt[HC / 2];
 #pragma unroll
-                        for (int j = 0; j < HC; ++j) {
-                            ln_s1 += v[j];
-                            ln_s2 = fmaf(v[j], v[j], ln_s2);
+                        for (int q = 0; q < HC / 4; ++q) {
+                            const float4 gmm = __ldg(reinterpret_cast<const float4*>(ep.lnp_gamma + c0) + q);
+                            const float y0 = v[4 * q] - ln_c, y1 = v[4 * q + 1] - ln_c, y2 = v[4 * q + 2] - ln_c,
+                                        y3 = v[4 * q + 3] - ln_c;
+                            ln_s1 += (y0 + y1) + (y2 + y3);
+                            ln_s2 = fmaf(y0, y0, fmaf(y1, y1, fmaf(y2, y2, fmaf(y3, y3, ln_s2))));
+                            xt[2 * q] = pack_h2(y0 * gmm.x, y1 * gmm.y);
+                            xt[2 * q + 1] = pack_h2(y2 * gmm.z, y3 * gmm.w);
                         }
+                        // one 256-bit store: the thread's 32 bytes are one full sector of its row
+                        static_assert(HC == 16 || !OUT_F32, "xt slice = 16 columns per thread");
+                        asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ep.lnp_xt + (size_t)gm * N + c0),
+                                     "r"(xt[0]), "r"(xt[1]), "r"(xt[2]), "r"(xt[3]), "r"(xt[4]), "r"(xt[5]), "r"(xt[6]), "r"(xt[7])
+                                     : "memory");
                     }
                 } else {
                     // fp16 slab row = 64 columns = 8 units of 8; this thread fills units 4*half .. 4*half+3
@@ -673,67 +726,10 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                 }
             }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            if constexpr (OUT_F32) {
-                if (by_rows && nt == n_tiles - 1) {
-                    // ---- the 128 rows of this CTA are complete: finish LayerNorm (clip/model.py:153-159) ----
-                    ln_stats[r * 2 + half] = make_float2(ln_s1, ln_s2);
-                    ln_s1 = ln_s2 = 0.f;
-                    if (issuer && !(ep.ln_dbg & 2)) {
-                        tma_store_wait_all();  // the row block has reached L2 (completion, not just the smem reads)
-                        asm volatile("fence.proxy.async.global;" ::: "memory");
-                    }
-                    gemm_bar_sync256();
-                    const int ew = warp - 2;       // 8 warps x 16 rows; a warp reads 512 contiguous bytes of one row
-                    const int nchunk = N >> 7;     // 128-column chunks of a row (N % 256 == 0, N <= 1024)
-                    const float inv_n = 1.f / (float)N;
-#pragma unroll 1
-                    for (int i = (ep.ln_dbg & 1) ? 16 : 0; i < 16; i += 2) {
-                        const int r0 = ew * 16 + i;
-                        const int gm0 = m0 + r0, gm1 = gm0 + 1;
-                        float4 xa[8], xb[8];
-                        const float* pa = ep.ln_x + (size_t)gm0 * ep.ln_ldx + lane * 4;
-                        const float* pb = pa + ep.ln_ldx;
-#pragma unroll
-                        for (int ch = 0; ch < 8; ++ch)
-                            if (ch < nchunk) {
-                                if (gm0 < M) xa[ch] = __ldcg(reinterpret_cast<const float4*>(pa + ch * 128));
-                                if (gm1 < M) xb[ch] = __ldcg(reinterpret_cast<const float4*>(pb + ch * 128));
-                            }
-                        const float2 a0 = ln_stats[r0 * 2], a1 = ln_stats[r0 * 2 + 1];
-                        const float2 b0 = ln_stats[r0 * 2 + 2], b1 = ln_stats[r0 * 2 + 3];
-                        const float mean_a = (a0.x + a1.x) * inv_n, mean_b = (b0.x + b1.x) * inv_n;
-                        const float rstd_a = rsqrtf(fmaxf((a0.y + a1.y) * inv_n - mean_a * mean_a, 0.f) + ep.ln_eps);
-                        const float rstd_b = rsqrtf(fmaxf((b0.y + b1.y) * inv_n - mean_b * mean_b, 0.f) + ep.ln_eps);
-                        __half* ya = ep.ln_out + (size_t)gm0 * N + lane * 4;
-                        __half* yb = ya + N;
-#pragma unroll
-                        for (int ch = 0; ch < 8; ++ch)
-                            if (ch < nchunk) {
-                                // gamma / beta: 2 x 16 bytes per lane and chunk out of L1 (the same 2N floats for every row)
-                                const float4 gm = __ldg(reinterpret_cast<const float4*>(ep.ln_gamma + ch * 128 + lane * 4));
-                                const float4 bt = __ldg(reinterpret_cast<const float4*>(ep.ln_beta + ch * 128 + lane * 4));
-                                if (gm0 < M) {
-                                    const float4 x = xa[ch];
-                                    uint2 o;
-                                    o.x = pack_h2(fmaf((x.x - mean_a) * rstd_a, gm.x, bt.x),
-                                                  fmaf((x.y - mean_a) * rstd_a, gm.y, bt.y));
-                                    o.y = pack_h2(fmaf((x.z - mean_a) * rstd_a, gm.z, bt.z),
-                                                  fmaf((x.w - mean_a) * rstd_a, gm.w, bt.w));
-                                    *reinterpret_cast<uint2*>(ya + ch * 128) = o;
-                                }
-                                if (gm1 < M) {
-                                    const float4 x = xb[ch];
-                                    uint2 o;
-                                    o.x = pack_h2(fmaf((x.x - mean_b) * rstd_b, gm.x, bt.x),
-                                                  fmaf((x.y - mean_b) * rstd_b, gm.y, bt.y));
-                                    o.y = pack_h2(fmaf((x.z - mean_b) * rstd_b, gm.z, bt.z),
-                                                  fmaf((x.w - mean_b) * rstd_b, gm.w, bt.w));
-                                    *reinterpret_cast<uint2*>(yb + ch * 128) = o;
-                                }
-                            }
-                    }
-                    gemm_bar_sync256();  // ln_stats is rewritten at the end of the next row block
-                }
+            if (lnp && gm < M) {
+                float* rec = ep.lnp_rec_out + (size_t)gm * kLnRec;
+                *reinterpret_cast<float2*>(rec + 2 * (2 * (tile % n_tiles) + half)) = make_float2(ln_s1, ln_s2);
+                if (n0 == 0 && half == 0) rec[kLnRecC] = ln_c;
             }
         }
         if (issuer) tma_store_wait_all();

@@ -360,12 +360,53 @@ __device__ __forceinline__ float4 drop_scale4(unsigned long long bits, unsigned 
 }
 
 // x[b, 1+j] = prompt[j]  (deep prompt replacement before block l >= 1), times the dropout keep mask / (1-p) when thr > 0
-// With h != nullptr the LayerNorm of the new rows (the ln_1 of the block about to run) is written to h as well: the
-// fused-LayerNorm GEMM of the previous block normalised the rows this kernel replaces.
+// xt / record of a row held in registers, for the LayerNorm carried through the linears (gemm_sm100.cuh): xt = (x - mean) *
+// gamma as fp16; record = first (sum, sum of squares) pair (0, M2), the other pairs 0, centring value = mean.
+__device__ __forceinline__ void row_ln_carry(Row& row, const float* __restrict__ gamma, __half* __restrict__ xt_row,
+                                             float* __restrict__ rec_row, int d, int lane) {
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) s += row.v[i].x + row.v[i].y + row.v[i].z + row.v[i].w;
+    const float mean = wsum(s) / d;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < kMaxV4; ++i) {
+        const int c = i * 128 + lane * 4;
+        if (c < d) {
+            const float4 gg = *reinterpret_cast<const float4*>(gamma + c);
+            const float a = row.v[i].x - mean, b = row.v[i].y - mean, e = row.v[i].z - mean, f = row.v[i].w - mean;
+            q += a * a + b * b + e * e + f * f;
+            row.v[i] = make_float4(a * gg.x, b * gg.y, e * gg.z, f * gg.w);
+        }
+    }
+    q = wsum(q);
+    row_store_h(row, xt_row, d, lane);
+    if (lane < 5) {  // 20 floats: pairs 0..7, then c at index 16
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane == 0) o.y = q;
+        if (lane == 4) o.x = mean;
+        reinterpret_cast<float4*>(rec_row)[lane] = o;
+    }
+}
+
+// Starts the chain: xt / records of plain fp32 rows.
+__global__ void ln_prep_kernel(const float* __restrict__ x, const float* __restrict__ gamma, __half* __restrict__ xt,
+                               float* __restrict__ rec, int rows, int d) {
+    pdl_sync();
+    const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    Row row;
+    row_load(row, x + (size_t)r * d, d, lane);
+    row_ln_carry(row, gamma, xt + (size_t)r * d, rec + (size_t)r * 20, d, lane);
+}
+
+// With xt != nullptr the xt / records of the new rows are written as well: the previous block's FC2 produced them for
+// the rows this kernel replaces.
 __global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __restrict__ prompt, int prompt_f16, int B,
                                        int L, int v, int d, unsigned thr, float keep_scale, unsigned long long seed,
-                                       int slab, __half* __restrict__ h, const float* __restrict__ gamma,
-                                       const float* __restrict__ beta, float eps) {
+                                       int slab, __half* __restrict__ xt, float* __restrict__ rec,
+                                       const float* __restrict__ gamma) {
     const int r = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (r >= B * v) return;
@@ -383,13 +424,9 @@ __global__ void set_prompt_rows_kernel(float* __restrict__ x, const void* __rest
             }
         }
     }
-    row_store(row, x + ((size_t)b * L + 1 + j) * d, d, lane);
-    if (h) {
-        float mean, rstd;
-        row_stats(row, d, lane, eps, mean, rstd);
-        row_affine(row, gamma, beta, d, lane, mean, rstd);
-        row_store_h(row, h + ((size_t)b * L + 1 + j) * d, d, lane);
-    }
+    const size_t ro = (size_t)b * L + 1 + j;
+    row_store(row, x + ro * d, d, lane);
+    if (xt) row_ln_carry(row, gamma, xt + ro * d, rec + ro * 20, d, lane);
 }
 
 // keep[b, j, c] in {0,1}: the mask the two kernels above/below apply (for tests and for replaying a step elsewhere)
@@ -629,15 +666,13 @@ int drop_params(float p, const char* who, unsigned& thr, float& keep_scale) {
 
 int mvlpt_set_prompt_rows(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
                           uint64_t seed, int slab, mvlpt_stream_t stream) {
-    return mvlpt_set_prompt_rows_ln(x, prompt, prompt_f16, B, L, v, d, drop_p, seed, slab, nullptr, nullptr, nullptr, 0.f,
-                                    stream);
+    return mvlpt_set_prompt_rows_ln(x, prompt, prompt_f16, B, L, v, d, drop_p, seed, slab, nullptr, nullptr, nullptr, stream);
 }
 
 int mvlpt_set_prompt_rows_ln(void* x, const void* prompt, int prompt_f16, int B, int L, int v, int d, float drop_p,
-                             uint64_t seed, int slab, void* h, const void* gamma, const void* beta, float eps,
-                             mvlpt_stream_t stream) {
+                             uint64_t seed, int slab, void* xt, void* rec, const void* gamma, mvlpt_stream_t stream) {
     if (!x || !prompt) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows: null argument");
-    if (h && (!gamma || !beta)) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows_ln: h needs gamma and beta");
+    if (xt && (!gamma || !rec)) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows_ln: xt needs rec and gamma");
     if (B <= 0 || v <= 0 || L < 1 + v) return fail(MVLPT_EINVAL, "mvlpt_set_prompt_rows: bad sizes");
     int rc = check_d(d, "mvlpt_set_prompt_rows");
     if (rc) return rc;
@@ -646,9 +681,21 @@ int mvlpt_set_prompt_rows_ln(void* x, const void* prompt, int prompt_f16, int B,
     if ((rc = drop_params(drop_p, "mvlpt_set_prompt_rows", thr, ks))) return rc;
     if ((rc = require_sm100())) return rc;
     set_prompt_rows_kernel<<<cdiv(B * v, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-        static_cast<float*>(x), prompt, prompt_f16, B, L, v, d, thr, ks, seed, slab, static_cast<__half*>(h),
-        static_cast<const float*>(gamma), static_cast<const float*>(beta), eps);
+        static_cast<float*>(x), prompt, prompt_f16, B, L, v, d, thr, ks, seed, slab, static_cast<__half*>(xt),
+        static_cast<float*>(rec), static_cast<const float*>(gamma));
     return launched("set_prompt_rows");
+}
+
+int mvlpt_ln_prep(const void* x, const void* gamma, void* xt, void* rec, int rows, int d, mvlpt_stream_t stream) {
+    if (!x || !gamma || !xt || !rec) return fail(MVLPT_EINVAL, "mvlpt_ln_prep: null argument");
+    if (rows <= 0) return fail(MVLPT_EINVAL, "mvlpt_ln_prep: rows must be positive");
+    int rc = check_d(d, "mvlpt_ln_prep");
+    if (rc) return rc;
+    if ((rc = require_sm100())) return rc;
+    MVLPT_CUDA_OK(launch_pdl(ln_prep_kernel, dim3(cdiv(rows, 8)), dim3(256), 0, static_cast<cudaStream_t>(stream), 1,
+                             static_cast<const float*>(x), static_cast<const float*>(gamma), static_cast<__half*>(xt),
+                             static_cast<float*>(rec), rows, d));
+    return launched("ln_prep");
 }
 
 int mvlpt_prompt_grad(void* dx, void* dx16, void* grad, int B, int L, int v, int d, float inv_scale, int zero_rows,

@@ -54,6 +54,13 @@ class BlockWeights:
         self.w_fc, self.b_fc = h("mlp.c_fc.weight"), h("mlp.c_fc.bias")
         self.w_pr, self.b_pr = h("mlp.c_proj.weight"), h("mlp.c_proj.bias")
         self.w_qkv_t = self.w_o_t = self.w_fc_t = self.w_pr_t = None
+        # LayerNorm carried through the linears (csrc/gemm_sm100.cuh): LN(x).W^T + b = rstd*(xt.W^T - (mu-c)*sg) + bp with
+        # sg[n] = sum_k gamma[k] W[n,k], bp[n] = b[n] + sum_k beta[k] W[n,k] — summed in fp32, stored like the biases (fp16), once
+        # per layer at load time
+        self.sg_qkv = (self.w_qkv.float() @ self.ln1_g).to(F16).contiguous()
+        self.bp_qkv = (self.b_qkv.float() + self.w_qkv.float() @ self.ln1_b).to(F16).contiguous()
+        self.sg_fc = (self.w_fc.float() @ self.ln2_g).to(F16).contiguous()
+        self.bp_fc = (self.b_fc.float() + self.w_fc.float() @ self.ln2_b).to(F16).contiguous()
 
     def ensure_transposed(self):
         """[in, out] copies: the W operand of dA = dY . W (dgrad); only towers that train need them."""
@@ -75,7 +82,8 @@ class TowerBuffers:
         nsave = layers if train else 1
         self.x = [e(M, d, dt=F32) for _ in range(layers + 1 if train else 1)]
         self.xmid = [e(M, d, dt=F32) for _ in range(nsave)] if train else self.x
-        self.h = e(M, d)
+        self.h = e(M, d)  # LayerNorm output, or xt = (x - c) * gamma when the linears carry the LayerNorm
+        self.rec = [e(M, ops.LN_REC, dt=F32) for _ in range(2)]  # row records of the block input / of x after attention
         self.qkv = [e(M, 3 * d) for _ in range(nsave)]
         self.o = [e(M, d) for _ in range(nsave)]
         self.lse = [e(N, heads, L, dt=F32) for _ in range(nsave)]
@@ -104,25 +112,31 @@ class TowerBuffers:
 def block_forward(w: BlockWeights, a: TowerBuffers, l: int, causal: bool, h_ready: bool = False, next_ln=None) -> bool:
     """x += attn(ln_1(x)); x += mlp(ln_2(x))   — clip/model.py:185-188.
 
-    Five launches when the shape allows the fused LayerNorm (ops.gemm_ln_supported): QKV, attention, out-proj (+ residual
-    + ln_2), FC1 (+ QuickGELU), FC2 (+ residual + the NEXT block's ln_1 when `next_ln` = (gamma, beta) is given).
-    `h_ready`: a.h already holds ln_1(x) (written by the previous block's FC2).  Returns whether a.h holds `next_ln`
-    of the output on exit."""
+    When the shape allows it (ops.gemm_ln_supported) no LayerNorm kernel runs: the residual-stream linears (out-proj, FC2)
+    emit xt = (x - c) * gamma and the row records, the QKV / FC1 linears finish the LayerNorm in their epilogue — five
+    launches per block: QKV, attention, out-proj, FC1 (+ QuickGELU), FC2.  `next_ln` = gamma of the LayerNorm that will
+    read this block's output (the next block's ln_1); `h_ready`: a.h / a.rec[0] already hold xt / records of the input
+    (written by the previous block's FC2).  Returns whether they hold those of the output on exit."""
     M, d, i = a.M, a.d, a.idx(l)
     xin, xmid, xout = a.x_in(l), a.x_mid(l), a.x_out(l)
-    fuse = ops.gemm_ln_supported(M, d)
-    if not h_ready:
+    aux = a.t[i] if a.train else None
+    if not ops.gemm_ln_supported(M, d):
         ops.ln_fwd(xin, w.ln1_g, w.ln1_b, a.h, M, d)
-    ops.gemm(a.h, w.w_qkv, a.qkv[i], bias=w.b_qkv)
-    ops.fmha_fwd(a.qkv[i], a.o[i], a.lse[i], a.N, a.L, d, a.heads, causal)
-    if fuse:
-        ops.gemm(a.o[i], w.w_o, xmid, bias=w.b_o, resid=xin, ln=(w.ln2_g, w.ln2_b, a.h))
-    else:
+        ops.gemm(a.h, w.w_qkv, a.qkv[i], bias=w.b_qkv)
+        ops.fmha_fwd(a.qkv[i], a.o[i], a.lse[i], a.N, a.L, d, a.heads, causal)
         ops.gemm(a.o[i], w.w_o, xmid, bias=w.b_o, resid=xin)
         ops.ln_fwd(xmid, w.ln2_g, w.ln2_b, a.h, M, d)
-    ops.gemm(a.h, w.w_fc, a.g, bias=w.b_fc, act=ops.ACT_QUICKGELU, aux_out=a.t[i] if a.train else None)
-    if fuse and next_ln is not None:
-        ops.gemm(a.g, w.w_pr, xout, bias=w.b_pr, resid=xmid, ln=(next_ln[0], next_ln[1], a.h))
+        ops.gemm(a.h, w.w_fc, a.g, bias=w.b_fc, act=ops.ACT_QUICKGELU, aux_out=aux)
+        ops.gemm(a.g, w.w_pr, xout, bias=w.b_pr, resid=xmid)
+        return False
+    if not h_ready:
+        ops.ln_prep(xin, w.ln1_g, a.h, a.rec[0], M, d)
+    ops.gemm(a.h, w.w_qkv, a.qkv[i], ln_cons=(a.rec[0], w.sg_qkv, w.bp_qkv))
+    ops.fmha_fwd(a.qkv[i], a.o[i], a.lse[i], a.N, a.L, d, a.heads, causal)
+    ops.gemm(a.o[i], w.w_o, xmid, bias=w.b_o, resid=xin, ln_prod=(a.rec[0], a.rec[1], w.ln2_g, a.h))
+    ops.gemm(a.h, w.w_fc, a.g, act=ops.ACT_QUICKGELU, aux_out=aux, ln_cons=(a.rec[1], w.sg_fc, w.bp_fc))
+    if next_ln is not None:
+        ops.gemm(a.g, w.w_pr, xout, bias=w.b_pr, resid=xmid, ln_prod=(a.rec[1], a.rec[0], next_ln, a.h))
         return True
     ops.gemm(a.g, w.w_pr, xout, bias=w.b_pr, resid=xmid)
     return False
@@ -223,10 +237,9 @@ class ImageTower:
                 if a.train and last is not src:
                     src.copy_(last)  # only reachable through the skipped-layer quirk
                 ops.set_prompt_rows(src, vpt_deep[l - 1], B, a.L, v, self.d, drop_p, drop_seed, l,
-                                    ln=(blk.ln1_g, blk.ln1_b, a.h) if h_ready else None)
+                                    ln=(a.h, a.rec[0], blk.ln1_g) if h_ready else None)
             nxt = self.blocks[run[k + 1]] if k + 1 < len(run) else None
-            h_ready = block_forward(blk, a, l, causal=False, h_ready=h_ready,
-                                    next_ln=None if nxt is None else (nxt.ln1_g, nxt.ln1_b))
+            h_ready = block_forward(blk, a, l, causal=False, h_ready=h_ready, next_ln=None if nxt is None else nxt.ln1_g)
             last = a.x_out(l)
         bf["final"] = last
         bf["run"] = run
@@ -307,7 +320,7 @@ class TextTower:
         for l in range(self.layers):
             nxt = self.blocks[l + 1] if l + 1 < self.layers else None
             h_ready = block_forward(self.blocks[l], a, l, causal=True, h_ready=h_ready,
-                                    next_ln=None if nxt is None else (nxt.ln1_g, nxt.ln1_b))
+                                    next_ln=None if nxt is None else nxt.ln1_g)
         bf["final"] = a.x_out(self.layers - 1)
         ops.ln_fwd(bf["final"], self.ln_g, self.ln_b, bf["pooled"], N, d, row_index=eot_rows, hilo=True)
         ops.gemm(bf["pooled"], self.proj_t2, bf["feat"])

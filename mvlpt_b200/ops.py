@@ -16,6 +16,7 @@ from ._lib import GemmDesc, check
 
 ACT_NONE, ACT_QUICKGELU, ACT_MUL_DQUICKGELU = 0, 1, 2
 LN_EPS = 1e-5
+LN_REC = _lib.LN_REC  # floats per row record of the LayerNorm-carrying GEMM chain
 
 
 class Profiler:
@@ -65,15 +66,16 @@ def _chk(t: torch.Tensor, dtype, name: str):
                               f"contig={t.is_contiguous()}")
 
 
-def gemm_ln_supported(M: int, N: int) -> bool:
-    """Can the residual-stream linear of this shape carry the following LayerNorm (mvlpt_gemm_ln)?"""
-    return bool(_lib.lib().mvlpt_gemm_ln_supported(int(M), int(N)))
+def gemm_ln_supported(M: int, width: int) -> bool:
+    """Can the linears around a LayerNorm of `width`-wide rows carry it (mvlpt_gemm_ln) for M rows?"""
+    return bool(_lib.lib().mvlpt_gemm_ln_supported(int(M), int(width)))
 
 
 def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid=None, alpha=1.0,
-         M=None, N=None, K=None, lda=None, ldw=None, ld_out=None, ld_aux=None, ln=None):
-    """out[M,N] = epi(alpha * A[M,K] @ W[N,K]^T); see include/mvlpt_sm100.h:mvlpt_gemm.
-    ln=(gamma, beta, h): also h = LayerNorm(out) * gamma + beta as fp16 (mvlpt_gemm_ln)."""
+         M=None, N=None, K=None, lda=None, ldw=None, ld_out=None, ld_aux=None, ln_prod=None, ln_cons=None):
+    """out[M,N] = epi(alpha * A[M,K] @ W[N,K]^T); see include/mvlpt_sm100.h:mvlpt_gemm / mvlpt_gemm_ln.
+    ln_prod=(rec_in | None, rec_out, gamma, xt): the residual-stream linear also emits xt = (out - c) * gamma and the row
+    records of `out`.  ln_cons=(rec, sg, bp): A is such an xt; the LayerNorm is finished in the epilogue (bias in bp)."""
     _chk(A, torch.float16, "gemm A")
     _chk(W, torch.float16, "gemm W")
     M = A.shape[0] if M is None else M
@@ -89,23 +91,47 @@ def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid
         raise _lib.MvlptError("gemm out must be fp16 or fp32")
     d = GemmDesc(M, N, K, lda, ldw, ld_out, ld_aux, act, out_f32, float(alpha))
     t0 = PROFILER.begin() if PROFILER is not None else None
-    if ln is not None:
-        g_, b_, h_ = ln
-        _chk(h_, torch.float16, "gemm ln_out")
-        if aux is not None or alpha != 1.0:
-            raise _lib.MvlptError("gemm: the fused LayerNorm goes with the plain residual epilogue only")
-        check(_lib.lib().mvlpt_gemm_ln(byref(d), _p(A), _p(W), _p(bias), _p(resid), _p(out), _p(g_), _p(b_), _p(h_), LN_EPS,
-                                       _stream()), "mvlpt_gemm_ln")
+    tag = ""
+    if ln_prod is not None or ln_cons is not None:
+        c = _lib.LnCarry()
+        if ln_prod is not None:
+            rec_in, rec_out, gamma, xt = ln_prod
+            _chk(xt, torch.float16, "gemm xt")
+            c.rec_in, c.rec_out, c.gamma, c.xt = _pv(rec_in), _pv(rec_out), _pv(gamma), _pv(xt)
+            c.width, tag = N, ",lnp=1"
+        else:
+            rec, sg, bp = ln_cons
+            if bias is not None:
+                raise _lib.MvlptError("gemm: with ln_cons the bias is folded into bp")
+            _chk(sg, torch.float16, "gemm sg")
+            _chk(bp, torch.float16, "gemm bp")
+            c.rec, c.sg, bias = _pv(rec), _pv(sg), bp
+            c.width, tag = K, ",lnc=1"
+        c.eps = LN_EPS
+        check(_lib.lib().mvlpt_gemm_ln(byref(d), _p(A), _p(W), _p(bias), _p(aux_in), _p(aux_out), _p(resid), _p(out),
+                                       byref(c), _stream()), "mvlpt_gemm_ln")
     else:
         check(_lib.lib().mvlpt_gemm(byref(d), _p(A), _p(W), _p(bias), _p(aux_in), _p(aux_out), _p(resid), _p(out),
                                     _stream()), "mvlpt_gemm")
     if t0 is not None:
         nbytes = 2.0 * (M * K + N * K) + (4.0 if out_f32 else 2.0) * M * N + (4.0 * M * N if resid is not None else 0.0) \
-            + (2.0 * M * N if aux is not None else 0.0) + (2.0 * M * N if ln is not None else 0.0)
+            + (2.0 * M * N if aux is not None else 0.0) + (2.0 * M * N if ln_prod is not None else 0.0)
         PROFILER.end("gemm_f16_tn", t0, 2.0 * M * N * K, nbytes)
-        PROFILER.records.append((f"gemm[M={M},N={N},K={K},act={act},f32={out_f32},resid={int(resid is not None)}"
-                                 f"{',ln=1' if ln is not None else ''}]", *PROFILER.records[-1][1:]))
+        PROFILER.records.append((f"gemm[M={M},N={N},K={K},act={act},f32={out_f32},resid={int(resid is not None)}{tag}]",
+                                 *PROFILER.records[-1][1:]))
     return out
+
+
+def _pv(t):
+    return None if t is None else t.data_ptr()
+
+
+def ln_prep(x, gamma, xt, rec, rows, d):
+    """xt = (x - mean) * gamma (fp16) and the row records that start a LayerNorm-carrying GEMM chain (mvlpt_ln_prep)."""
+    t0 = PROFILER.begin() if PROFILER is not None else None
+    check(_lib.lib().mvlpt_ln_prep(_p(x), _p(gamma), _p(xt), _p(rec), rows, d, _stream()), "mvlpt_ln_prep")
+    if t0 is not None:
+        PROFILER.end("ln_fwd", t0, 0.0, 6.0 * rows * d)
 
 
 def fmha_fwd(qkv, out, lse, N, L, d, heads, causal):
@@ -156,11 +182,11 @@ def embed_assemble(pe, cls, pos, gamma, beta, prompt, x0, B, G, v, d):
 
 
 def set_prompt_rows(x, prompt, B, L, v, d, drop_p=0.0, seed=0, slab=0, ln=None):
-    """ln=(gamma, beta, h): also h[rows] = LayerNorm(new rows) (the fused-LayerNorm path, mvlpt_set_prompt_rows_ln)."""
-    g_, b_, h_ = ln if ln is not None else (None, None, None)
+    """ln=(xt, rec, gamma): also the xt / row records of the new rows (mvlpt_set_prompt_rows_ln)."""
+    xt, rec, g_ = ln if ln is not None else (None, None, None)
     check(_lib.lib().mvlpt_set_prompt_rows_ln(_p(x), _p(prompt), int(prompt.dtype == torch.float16), B, L, v, d,
-                                              float(drop_p), int(seed), int(slab), _p(h_), _p(g_), _p(b_), LN_EPS,
-                                              _stream()), "mvlpt_set_prompt_rows")
+                                              float(drop_p), int(seed), int(slab), _p(xt), _p(rec), _p(g_), _stream()),
+          "mvlpt_set_prompt_rows")
 
 
 def dropout_keep(keep, B, v, d, drop_p, seed, slab):

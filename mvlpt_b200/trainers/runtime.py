@@ -84,10 +84,13 @@ def _merge(node: NS, d: dict, path: str = ""):
                 setattr(node, k, NS())
             _merge(getattr(node, k), v, f"{path}{k}.")
         else:
-            if isinstance(v, str) and v.startswith("(") and v.endswith(")"):
+            if isinstance(v, str):
+                # yacs' _decode_cfg_value: strings that are Python literals become them ("(224, 224)" -> tuple,
+                # "1e-5" -> float — PyYAML's YAML-1.1 resolver leaves that one a string)
+                import ast
                 try:
-                    v = tuple(int(x) for x in v[1:-1].split(",") if x.strip())
-                except ValueError:
+                    v = ast.literal_eval(v)
+                except (ValueError, SyntaxError):
                     pass
             setattr(node, k, v)
 

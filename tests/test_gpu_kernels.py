@@ -42,42 +42,69 @@ def test_gemm(M, N, K, act, resid, f32):
     assert _rel(out.float(), ref) < 2e-3
 
 
-@pytest.mark.parametrize("M,N,K,inplace", [
-    (256, 768, 768, False), (410, 768, 768, False), (515, 512, 2048, True), (1000, 1024, 1024, False),
-    (52480, 768, 768, True), (52480, 768, 3072, False), (25000, 512, 512, False), (300, 256, 64, False),
-    (41 * 256 + 7, 768, 768, False),  # more row blocks than CTA pairs is not needed for the ragged last block
-    (74 * 256 * 2 + 130, 512, 512, True),  # every pair owns several row blocks, the last one ragged
-])
-def test_gemm_with_fused_layernorm(M, N, K, inplace):
-    """mvlpt_gemm_ln: out = A.W^T + b + resid (fp32) and h = LayerNorm(out)*gamma+beta (fp16) from one kernel, against
-    torch's two-pass layer_norm of the same fp32 rows; rows with a large mean exercise the sum-of-squares statistics."""
+@pytest.mark.parametrize("M,d,inplace", [(256, 768, False), (410, 768, False), (515, 512, True), (1000, 1024, False),
+                                         (52480, 768, True), (25000, 512, False), (300, 256, False),
+                                         (74 * 512 + 130, 512, True)])
+def test_layernorm_carried_through_the_linears(M, d, inplace):
+    """mvlpt_gemm_ln: the chain  ln_prep -> consumer GEMM -> ... -> producer GEMM (+xt, row records) -> consumer GEMM
+    against the explicit path (LayerNorm kernel, plain GEMMs) and against torch's two-pass layer_norm in fp32.  Rows with
+    a large mean exercise the centring; the second consumer reads what the producer's epilogue wrote."""
     from mvlpt_b200 import ops
-    assert ops.gemm_ln_supported(M, N)
-    assert not ops.gemm_ln_supported(255, N) and not ops.gemm_ln_supported(M, 128) and not ops.gemm_ln_supported(M, 1280)
+    F = torch.nn.functional
+    assert ops.gemm_ln_supported(M, d)
+    assert not ops.gemm_ln_supported(255, d) and not ops.gemm_ln_supported(M, 128) and not ops.gemm_ln_supported(M, 1280)
     torch.manual_seed(0)
     dev = "cuda"
-    A = (torch.randn(M, K, device=dev) * 0.5).half()
-    W = (torch.randn(N, K, device=dev) * 0.05).half()
-    b = (torch.randn(N, device=dev) * 0.1).half()
-    r = torch.randn(M, N, device=dev) * 2
-    r[::7] += 6.0   # rows whose mean is several standard deviations from zero
-    gamma = torch.randn(N, device=dev) * 0.1 + 1
-    beta = torch.randn(N, device=dev) * 0.1
-    ref = A.float() @ W.float().t() + b.float() + r
-    out = r.clone() if inplace else torch.full((M, N), float("nan"), device=dev)
-    h = torch.full((M, N), float("nan"), device=dev, dtype=torch.half)
-    ops.gemm(A, W, out, bias=b, resid=out if inplace else r, ln=(gamma, beta, h))
-    assert not torch.isnan(out).any() and not torch.isnan(h).any()
-    assert _rel(out, ref) < 2e-3
-    # the LayerNorm of the rows the kernel itself produced: exact up to fp16 rounding of h
-    want = torch.nn.functional.layer_norm(out, (N,), gamma, beta, 1e-5)
-    assert _rel(h.float(), want) < 1.5e-3
-    # and identical (to fp16 rounding) to the stand-alone LayerNorm kernel on the same rows
-    h2 = torch.empty_like(h)
-    ops.ln_fwd(out, gamma, beta, h2, M, N)
-    assert (h.float() - h2.float()).abs().max() <= 2e-3 * want.abs().max()
-    with pytest.raises(Exception):
-        ops.gemm(A[:100], W, out[:100], bias=b, resid=r[:100], ln=(gamma, beta, h[:100]))
+    x = torch.randn(M, d, device=dev) * 2
+    x[::7] += 6.0   # rows whose mean is several standard deviations from zero
+    g1, b1 = torch.randn(d, device=dev) * 0.1 + 1, torch.randn(d, device=dev) * 0.1
+    g2, b2 = torch.randn(d, device=dev) * 0.1 + 1, torch.randn(d, device=dev) * 0.1
+    W1 = (torch.randn(3 * d, d, device=dev) * d ** -0.5).half()    # "QKV"
+    bias1 = (torch.randn(3 * d, device=dev) * 0.1).half()
+    Wo = (torch.randn(d, 3 * d, device=dev) * (3 * d) ** -0.5).half()  # stands in for attention + out-proj
+    bo = (torch.randn(d, device=dev) * 0.1).half()
+    W2 = (torch.randn(4 * d, d, device=dev) * d ** -0.5).half()    # "FC1"
+    bias2 = (torch.randn(4 * d, device=dev) * 0.1).half()
+    sg1, bp1 = (W1.float() @ g1).half(), (bias1.float() + W1.float() @ b1).half()
+    sg2, bp2 = (W2.float() @ g2).half(), (bias2.float() + W2.float() @ b2).half()
+    xt = torch.full((M, d), float("nan"), device=dev, dtype=torch.half)
+    rec0 = torch.full((M, ops.LN_REC), float("nan"), device=dev)
+    rec1 = torch.full((M, ops.LN_REC), float("nan"), device=dev)
+    # --- consumer after ln_prep
+    ops.ln_prep(x, g1, xt, rec0, M, d)
+    y1 = torch.full((M, 3 * d), float("nan"), device=dev, dtype=torch.half)
+    ops.gemm(xt, W1, y1, ln_cons=(rec0, sg1, bp1))
+    want1 = F.layer_norm(x, (d,), g1, b1, 1e-5) @ W1.float().t() + bias1.float()
+    assert not torch.isnan(y1).any()
+    assert _rel(y1.float(), want1) < 2e-3
+    h = torch.empty(M, d, device=dev, dtype=torch.half)
+    ops.ln_fwd(x, g1, b1, h, M, d)
+    y1e = torch.empty_like(y1)
+    ops.gemm(h, W1, y1e, bias=bias1)                     # the explicit path: same accuracy class
+    assert _rel(y1e.float(), want1) < 2e-3
+    assert _rel(y1.float(), want1) < 1.5 * _rel(y1e.float(), want1) + 2e-4
+    # --- producer: x2 = x + y1.Wo^T + bo, plus xt / records for the LayerNorm (g2, b2) that follows
+    x2 = x.clone() if inplace else torch.full((M, d), float("nan"), device=dev)
+    ops.gemm(y1, Wo, x2, bias=bo, resid=x2 if inplace else x, ln_prod=(rec0, rec1, g2, xt))
+    want_x2 = x + y1.float() @ Wo.float().t() + bo.float()
+    assert not torch.isnan(x2).any() and not torch.isnan(xt).any()
+    assert _rel(x2, want_x2) < 1e-3
+    used = 2 * (d // 128)
+    assert not torch.isnan(rec1[:, :used]).any() and not torch.isnan(rec1[:, 16]).any()
+    mean = rec1[:, 16] + rec1[:, 0:used:2].sum(1) / d
+    var = rec1[:, 1:used:2].sum(1) / d - (rec1[:, 0:used:2].sum(1) / d) ** 2
+    assert _rel(mean, x2.mean(1)) < 1e-5
+    assert _rel(var, x2.var(1, unbiased=False)) < 1e-4
+    assert (rec1[:, 16] - x.mean(1)).abs().max() < 1e-4 * x.abs().max()   # centred on the residual row's mean
+    # --- consumer of the producer's output
+    y2 = torch.full((M, 4 * d), float("nan"), device=dev, dtype=torch.half)
+    t2 = torch.full((M, 4 * d), float("nan"), device=dev, dtype=torch.half)
+    ops.gemm(xt, W2, y2, act=ops.ACT_QUICKGELU, aux_out=t2, ln_cons=(rec1, sg2, bp2))
+    pre = F.layer_norm(x2, (d,), g2, b2, 1e-5) @ W2.float().t() + bias2.float()
+    assert _rel(t2.float(), pre) < 2e-3
+    assert _rel(y2.float(), pre * torch.sigmoid(1.702 * pre)) < 2e-3
+    with pytest.raises(Exception):   # below one 256-row tile the CTA-pair kernel (and with it the carry) is not available
+        ops.gemm(xt[:100], W1, y1[:100], ln_cons=(rec0, sg1, bp1))
 
 
 @pytest.mark.parametrize("N,L,heads,causal", [(3, 197, 12, 0), (2, 205, 12, 0), (2, 50, 12, 0), (1, 257, 16, 0),

@@ -210,29 +210,29 @@ def test_cli_trains_resumes_and_evaluates(tmp_path, capsys):
     --model-dir --load-epoch reproduces the final test result."""
     from mvlpt_b200 import train as T
 
-    def run(*argv):
-        return T.main(T.build_parser().parse_args(list(argv)))
+    def run(*flags, opts=()):
+        # named flags first, free KEY VALUE options last (argparse.REMAINDER, exactly like the reference's train.py)
+        return T.main(T.build_parser().parse_args(list(flags) + list(base_opts) + list(opts)))
 
     common = ["--trainer", "MVLPT", "--synthetic", "--synthetic-classes", "6", "--synthetic-batches", "3", "--seed", "1",
-              "--backbone", "tiny", "--dataset-coop",
-              "TRAINER.MVLPT.VPT.N_CTX", "4", "TRAINER.MVLPT.COOP.N_CTX", "4", "TRAINER.MVLPT.PROJECT_METHOD", "identity",
-              "TRAINER.MVLPT.COOP.CLASS_TOKEN_POSITION", "end", "INPUT.SIZE", "(64, 64)",
-              "DATALOADER.TRAIN_X.BATCH_SIZE", "4", "DATALOADER.TEST.BATCH_SIZE", "5", "OPTIM.LR", "0.05",
-              "OPTIM.WARMUP_EPOCH", "0", "TEST.FINAL_MODEL", "best_val"]
+              "--backbone", "tiny", "--dataset-coop"]
+    base_opts = ["TRAINER.MVLPT.VPT.N_CTX", "4", "TRAINER.MVLPT.COOP.N_CTX", "4", "TRAINER.MVLPT.PROJECT_METHOD", "identity",
+                 "TRAINER.MVLPT.COOP.CLASS_TOKEN_POSITION", "end", "INPUT.SIZE", "(64, 64)",
+                 "DATALOADER.TRAIN_X.BATCH_SIZE", "4", "DATALOADER.TEST.BATCH_SIZE", "5", "OPTIM.LR", "0.05",
+                 "OPTIM.WARMUP_EPOCH", "0", "TEST.FINAL_MODEL", "best_val", "OPTIM.MAX_EPOCH", "3"]
     a, b = str(tmp_path / "a"), str(tmp_path / "b")
-    full = run(*common, "--output-dir", a, "OPTIM.MAX_EPOCH", "3")
+    full = run(*common, "--output-dir", a)
     assert (tmp_path / "a" / "prompt_learner" / "model.pth.tar-3").exists()
     assert (tmp_path / "a" / "prompt_learner" / "model-best.pth.tar").exists()
     assert isinstance(full.final_result, float)
-    # the schedule is a function of MAX_EPOCH: interrupt the same 3-epoch schedule after 2 epochs by checkpoint frequency
-    part = run(*common, "--output-dir", b, "OPTIM.MAX_EPOCH", "3", "TRAIN.CHECKPOINT_FREQ", "1", "TEST.NO_TEST", "True")
+    # interrupt the same 3-epoch schedule after 2 epochs: checkpoint every epoch, then pretend epoch 3 never happened
+    run(*common, "--output-dir", b, opts=["TRAIN.CHECKPOINT_FREQ", "1", "TEST.NO_TEST", "True"])
     import os
     os.remove(tmp_path / "b" / "prompt_learner" / "model.pth.tar-3")
     (tmp_path / "b" / "prompt_learner" / "checkpoint").write_text("model.pth.tar-2\n")
-    res = run(*common, "--output-dir", b, "--resume", b, "OPTIM.MAX_EPOCH", "3", "TEST.NO_TEST", "True")
+    res = run(*common, "--output-dir", b, "--resume", b, opts=["TEST.NO_TEST", "True"])
     assert res.start_epoch == 2
-    out = capsys.readouterr().out
-    assert "Previous epoch: 2" in out
+    assert "Previous epoch: 2" in capsys.readouterr().out
     ck_a = torch.load(tmp_path / "a" / "prompt_learner" / "model.pth.tar-3", weights_only=False)
     ck_b = torch.load(tmp_path / "b" / "prompt_learner" / "model.pth.tar-3", weights_only=False)
     for k, v in ck_a["state_dict"].items():
@@ -240,5 +240,5 @@ def test_cli_trains_resumes_and_evaluates(tmp_path, capsys):
     ev = run(*common, "--eval-only", "--model-dir", a, "--load-epoch", "3")
     with torch.no_grad():
         want = ev.test()
-    last = run(*common, "--output-dir", str(tmp_path / "c"), "OPTIM.MAX_EPOCH", "3", "TEST.FINAL_MODEL", "last_step")
+    last = run(*common, "--output-dir", str(tmp_path / "c"), opts=["TEST.FINAL_MODEL", "last_step"])
     assert abs(last.final_result - want) < 1e-6

@@ -83,29 +83,41 @@ if "gemm" in what:
         del A, out, r, ai, ao
 
 if "lnfuse" in what:
-    import os
-    for (M, N, K) in [(52480, 768, 768), (52480, 768, 3072), (50432, 768, 768), (50432, 768, 3072), (25000, 512, 512),
-                      (25000, 512, 2048), (2500, 512, 512), (2500, 512, 2048)]:
+    # explicit path (LayerNorm kernel + plain GEMMs) against the LayerNorm carried through the linears, per block half:
+    #   producer = residual-stream linear [M,d] (K = d: out-proj, K = 4d: FC2), consumer = QKV (N = 3d) / FC1 (N = 4d)
+    for (M, d) in [(52480, 768), (50432, 768), (25000, 512), (2500, 512), (16448, 1024)]:
         nb = 3
-        A = [(torch.randn(M, K, device=dev) * 0.5).half() for _ in range(nb)]
-        W = (torch.randn(N, K, device=dev) * 0.05).half()
-        b = (torch.randn(N, device=dev) * 0.1).half()
-        out = [torch.empty(M, N, device=dev) for _ in range(nb)]
-        r = [torch.randn(M, N, device=dev) for _ in range(nb)]
-        h = [torch.empty(M, N, device=dev, dtype=torch.half) for _ in range(nb)]
-        g = torch.ones(N, device=dev)
-        bb = torch.zeros(N, device=dev)
+        g = torch.ones(d, device=dev)
+        bb = torch.zeros(d, device=dev)
+        x = [torch.randn(M, d, device=dev) for _ in range(nb)]
+        xo = [torch.empty(M, d, device=dev) for _ in range(nb)]
+        h = [torch.empty(M, d, device=dev, dtype=torch.half) for _ in range(nb)]
+        rec0 = torch.zeros(M, ops.LN_REC, device=dev)
+        rec1 = torch.zeros(M, ops.LN_REC, device=dev)
+        ops.ln_prep(x[0], g, h[0], rec0, M, d)
         res = {}
-        t = timeit(lambda i: ops.gemm(A[i % nb], W, out[i % nb], bias=b, resid=r[i % nb]))
-        t_ln = timeit(lambda i: ops.ln_fwd(out[i % nb], g, bb, h[i % nb], M, N))
-        res["plain"], res["ln_kernel"] = t, t_ln
-        for dbg in ("0", "1", "2", "3"):
-            os.environ["MVLPT_LN_DBG"] = dbg
-            res["fused_dbg" + dbg] = timeit(lambda i: ops.gemm(A[i % nb], W, out[i % nb], bias=b, resid=r[i % nb],
-                                                               ln=(g, bb, h[i % nb])))
-        os.environ["MVLPT_LN_DBG"] = "0"
-        print(f"lnfuse M={M} N={N} K={K}: " + "  ".join(f"{k} {v:7.1f}" for k, v in res.items()), flush=True)
-        del A, out, r, h
+        for K in (d, 4 * d):
+            A = [(torch.randn(M, K, device=dev) * 0.5).half() for _ in range(nb)]
+            W = (torch.randn(d, K, device=dev) * 0.05).half()
+            b = (torch.randn(d, device=dev) * 0.1).half()
+            res[f"prod K={K} plain"] = timeit(lambda i: ops.gemm(A[i % nb], W, xo[i % nb], bias=b, resid=x[i % nb]))
+            res[f"prod K={K} carry"] = timeit(lambda i: ops.gemm(A[i % nb], W, xo[i % nb], bias=b, resid=x[i % nb],
+                                                                 ln_prod=(rec0, rec1, g, h[i % nb])))
+            del A
+        res["ln_kernel"] = timeit(lambda i: ops.ln_fwd(x[i % nb], g, bb, h[i % nb], M, d))
+        for N, act in ((3 * d, 0), (4 * d, 1)):
+            W = (torch.randn(N, d, device=dev) * 0.05).half()
+            b = (torch.randn(N, device=dev) * 0.1).half()
+            sg, bp = (W.float() @ g).half(), b
+            y = [torch.empty(M, N, device=dev, dtype=torch.half) for _ in range(nb)]
+            t = [torch.empty(M, N, device=dev, dtype=torch.half) for _ in range(nb)] if act else None
+            res[f"cons N={N} plain"] = timeit(lambda i: ops.gemm(h[i % nb], W, y[i % nb], bias=b, act=act,
+                                                                 aux_out=t[i % nb] if t else None))
+            res[f"cons N={N} carry"] = timeit(lambda i: ops.gemm(h[i % nb], W, y[i % nb], act=act,
+                                                                 aux_out=t[i % nb] if t else None, ln_cons=(rec1, sg, bp)))
+            del y, t
+        print(f"lnfuse M={M} d={d}: " + "  ".join(f"{k} {v:6.1f}" for k, v in res.items()), flush=True)
+        del x, xo, h
 
 if "ln" in what:
     for (M, d) in [(52480, 768), (7700, 512)]:
