@@ -88,7 +88,8 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
     uint64_t* acc_free = bars + 9;  // the epilogue warps have read the accumulators of a key chunk out of TMEM
     uint64_t* d_full = bars + 10;   // per-query statistics (D, lse) of a unit are in shared memory
     uint64_t* kv1_full = bars + 11; // {K1,V1} landed (load group 1 is requested in two parts: {Q1,dO1} is needed first)
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+    uint64_t* stats_free = bars + 12;  // the row warps have read the per-query statistics of a unit for the last time
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Lp = p.Lp, d = p.d, QT = p.QT, KC = p.KC, NQH = p.NQH;
@@ -113,6 +114,7 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
         mbar_init(acc_free, 128);
         mbar_init(d_full, 128);
         mbar_init(kv1_full, 1);
+        mbar_init(stats_free, kFmhaBwdRowThreads);
         mbar_fence_init();
     }
     if (warp == 1) {
@@ -352,6 +354,7 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     if ((qh & 1) || qh == NQH - 1) ++tci;
                 }
             }
+            mbar_arrive(stats_free);  // sD / sL2 of this unit may be overwritten
         }
     } else {
         // ============================== epilogue warps ==============================
@@ -424,12 +427,20 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
             for (int qt = 0; qt < QT; ++qt) row_stats(blockIdx.x, qt, Dn[qt], Ln[qt]);
             publish_stats(Dn, Ln);
         }
-        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x) {
+        int it = 0;
+        for (int unit = blockIdx.x; unit < p.num_units; unit += gridDim.x, ++it) {
             const int h = unit % p.heads, n = unit / p.heads;
             const int next = unit + gridDim.x;
             if (next < p.num_units)
                 for (int qt = 0; qt < QT; ++qt) row_stats(next, qt, Dn[qt], Ln[qt]);
             for (int kc = 0; kc < KC; ++kc) {
+                if (kc == KC - 1 && next < p.num_units) {
+                    // the statistics of the NEXT unit go out as soon as the row warps are through with this unit's —
+                    // before the accumulators of the last chunk are drained, so the next unit's first step does not wait
+                    // for this epilogue (in-kernel trace: 2-3 us per unit of 14 before)
+                    mbar_wait(stats_free, (uint32_t)it & 1);
+                    publish_stats(Dn, Ln);
+                }
                 mbar_wait(acc_full, gacc & 1);  // dK_kc, dV_kc (and, for the last chunk, dQ) complete: lanes = rows
                 ++gacc;
                 tc_fence_after();
@@ -460,7 +471,6 @@ fmha_bwd_tc_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_cons
                     if (QT > 1) load_row(kColDQ + 64, 0.125f, pq);
                     tc_fence_before();
                     mbar_arrive(acc_free);
-                    if (next < p.num_units) publish_stats(Dn, Ln);
                     fence_proxy_async_smem();
                     named_bar_sync(2, 128);
                     if (leader) {
