@@ -91,7 +91,8 @@ int mvlpt_gemm_ln(const mvlpt_gemm_desc* d, const void* A, const void* W, const 
 int mvlpt_ln_prep(const void* x, const void* gamma, void* xt, void* rec, int rows, int d, mvlpt_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
- * Attention core, head width 64 (d == heads*64), L <= 288, packed qkv [N*L, 3d] fp16 (Q | K | V).
+ * Attention core, head width 64 (d == heads*64), any L (tcgen05 kernels up to 272 / 256 rows forward / backward,
+ * streaming kernels beyond), packed qkv [N*L, 3d] fp16 (Q | K | V).
  * Replaces the inside of nn.MultiheadAttention (clip/model.py:171,181-183 -> F.multi_head_attention_forward:
  * q*hd^-1/2, QK^T, causal -inf mask for the text tower clip/model.py:324-330, softmax, PV) and its autograd.
  *   out  : fp16 [N*L, d]        lse : fp32 [N, heads, L]  (log-sum-exp of the scaled scores, saved for bwd)
@@ -101,9 +102,6 @@ int mvlpt_fmha_fwd(const void* qkv, void* out, void* lse, int N, int L, int d, i
                    mvlpt_stream_t stream);
 int mvlpt_fmha_bwd(const void* qkv, const void* o, const void* d_o, const void* lse, void* dqkv, int N, int L, int d,
                    int heads, int causal, mvlpt_stream_t stream);
-/* Test hook: on=1 routes the two calls above to the legacy mma.sync (HMMA) kernels kept as an on-GPU cross-check of
- * the tcgen05 kernels; returns the previous setting.  Never used by the product path. */
-int mvlpt_fmha_force_legacy(int on);
 
 /* ------------------------------------------------------------------------------------------------
  * LayerNorm with fp32 statistics (clip/model.py:153-159).  x: fp32 residual stream [*, d]; y: fp16 [rows, d].

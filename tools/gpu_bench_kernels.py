@@ -15,6 +15,8 @@ from mvlpt_b200 import ops  # noqa: E402
 dev = torch.device("cuda:0")
 torch.manual_seed(0)
 what = set(sys.argv[1:]) or {"fmha", "gemm", "ln"}
+if any(x.startswith("g") and x[1:].isdigit() for x in what):
+    what.add("gemm")
 ONE = "one" in what  # only the first case of each family, few iterations (for ncu captures)
 what.discard("one")
 
@@ -53,6 +55,7 @@ if "fmha" in what:
         del qkv, out, lse, do, dqkv
 
 if "gemm" in what:
+    only = [int(x[1:]) for x in what if x.startswith("g") and x[1:].isdigit()]
     cases = [
         # M, N, K, act, f32out, resid, aux_out
         (52480, 2304, 768, 0, 0, 0, 0), (52480, 768, 768, 0, 1, 1, 0), (52480, 3072, 768, 1, 0, 0, 1),
@@ -62,7 +65,7 @@ if "gemm" in what:
         (7700, 512, 2048, 0, 1, 1, 0), (7700, 2048, 512, 2, 0, 0, 0), (7700, 512, 2048, 0, 0, 0, 0),
         (7700, 512, 512, 0, 0, 0, 0), (7700, 512, 1536, 0, 0, 0, 0), (77000, 2048, 512, 1, 0, 0, 1),
     ]
-    for (M, N, K, act, f32, resid, aux) in ([cases[0], cases[2], cases[6]] if ONE else cases):
+    for (M, N, K, act, f32, resid, aux) in ([cases[0], cases[2], cases[6]] if ONE else ([cases[i] for i in only] if only else cases)):
         nb = 3
         A = [(torch.randn(M, K, device=dev) * 0.5).half() for _ in range(nb)]
         W = (torch.randn(N, K, device=dev) * 0.05).half()
