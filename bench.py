@@ -89,6 +89,8 @@ def parse_args():
     ap.add_argument("--no-eager-baseline", action="store_true")
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--gemm-log", default="", help="write the ordered shape keys of every GEMM launch of the process to "
+                                                   "this JSON file (tools/ncu_traffic.py matches an ncu capture to it)")
     ap.add_argument("--eval", action="store_true",
                     help="time the inference path (MVLPT.test's inner loop: parse_batch_test -> model_inference -> argmax; "
                          "SURVEY.md 8f-2) instead of the training step; not a BASELINE metric")
@@ -457,6 +459,8 @@ def ours_arm(a):
         raise SystemExit(f"--gpus {a.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {a.gpus}")
     _lib.check(_lib.lib().mvlpt_check_device(local_rank), "mvlpt_check_device")
 
+    if a.gemm_log:
+        ops.GEMM_LOG = []
     prob = make_problem(a)
     cfg = make_cfg(a)
     trainer = MVLPT(cfg, dm=prob.dm, clip_state_dict=prob.sd, device=dev, tokenized_prompts=prob.toks,
@@ -506,7 +510,8 @@ def ours_arm(a):
             out = step(batches[i % len(batches)])
         if a.eval:
             out.item()  # the evaluator's read of the batch result
-        trainer.finish_pending() if hasattr(trainer, "finish_pending") else None
+        if hasattr(out, "resolve"):
+            out.resolve()  # the host reads the last step's loss / accuracy (every step's were copied back asynchronously)
         e1.record()
         torch.cuda.synchronize()
         dp.barrier()
@@ -533,7 +538,9 @@ def ours_arm(a):
         e2e = {"value": world * B / (ms_e2e * 1e-3), "unit": "images/s", "ms_per_step": ms_e2e,
                "h2d_bytes_per_step": int(host_batches[0]["img"].numel() * 2 + host_batches[0]["label"].numel() * 8),
                "d2h_bytes_per_step": 8,
-               "loop": "MVLPT.run_epoch's: stage_batch(i+1) (pinned host -> device on the copy stream), then step i"}
+               "loop": "MVLPT.run_epoch's: stage_batch(i+1) (pinned host -> device on the copy stream), then step i; the "
+                       "loss / accuracy of every step are copied to pinned host memory asynchronously and the host reads "
+                       "the last one before the region ends"}
 
     # ---- FLOP accounting: the reference's algorithmic count, and what this step actually executes ----
     arch = synth.ARCHS[a.arch]
@@ -613,6 +620,8 @@ def ours_arm(a):
             r = run_cpu(a, prob, steps=2, warmup=1, budget_s=30.0)
             cpu = {"value": r["ips"], "unit": "images/s", "cores": r["cores"], "kind": r["kind"], "sample": r["sample"]}
 
+    if a.gemm_log and rank == 0:
+        Path(a.gemm_log).write_text(json.dumps(ops.GEMM_LOG))
     if rank == 0:
         line = {
             "metric": "inference images/sec (MVLPT.test inner loop)" if a.eval else "prompt-tuning images/sec",

@@ -50,6 +50,9 @@ class Profiler:
 
 
 PROFILER: Optional[Profiler] = None
+# When a list, every gemm() call appends its shape key: the n-th entry is the n-th GEMM kernel launch of the process
+# (tools/ncu_traffic.py matches an ncu capture of `-k regex:gemm_f16` against it).
+GEMM_LOG: Optional[list] = None
 
 
 def _p(t: Optional[torch.Tensor]):
@@ -91,14 +94,17 @@ def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid
         raise _lib.MvlptError("gemm out must be fp16 or fp32")
     d = GemmDesc(M, N, K, lda, ldw, ld_out, ld_aux, act, out_f32, float(alpha))
     t0 = PROFILER.begin() if PROFILER is not None else None
-    tag = ""
+    tag = ",lnp=1" if ln_prod is not None else (",lnc=1" if ln_cons is not None else "")
+    key = f"gemm[M={M},N={N},K={K},act={act},f32={out_f32},resid={int(resid is not None)}{tag}]"
+    if GEMM_LOG is not None:
+        GEMM_LOG.append(key)
     if ln_prod is not None or ln_cons is not None:
         c = _lib.LnCarry()
         if ln_prod is not None:
             rec_in, rec_out, gamma, xt = ln_prod
             _chk(xt, torch.float16, "gemm xt")
             c.rec_in, c.rec_out, c.gamma, c.xt = _pv(rec_in), _pv(rec_out), _pv(gamma), _pv(xt)
-            c.width, tag = N, ",lnp=1"
+            c.width = N
         else:
             rec, sg, bp = ln_cons
             if bias is not None:
@@ -106,7 +112,7 @@ def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid
             _chk(sg, torch.float16, "gemm sg")
             _chk(bp, torch.float16, "gemm bp")
             c.rec, c.sg, bias = _pv(rec), _pv(sg), bp
-            c.width, tag = K, ",lnc=1"
+            c.width = K
         c.eps = LN_EPS
         check(_lib.lib().mvlpt_gemm_ln(byref(d), _p(A), _p(W), _p(bias), _p(aux_in), _p(aux_out), _p(resid), _p(out),
                                        byref(c), _stream()), "mvlpt_gemm_ln")
@@ -117,8 +123,7 @@ def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid
         nbytes = 2.0 * (M * K + N * K) + (4.0 if out_f32 else 2.0) * M * N + (4.0 * M * N if resid is not None else 0.0) \
             + (2.0 * M * N if aux is not None else 0.0) + (2.0 * M * N if ln_prod is not None else 0.0)
         PROFILER.end("gemm_f16_tn", t0, 2.0 * M * N * K, nbytes)
-        PROFILER.records.append((f"gemm[M={M},N={N},K={K},act={act},f32={out_f32},resid={int(resid is not None)}{tag}]",
-                                 *PROFILER.records[-1][1:]))
+        PROFILER.records.append((key, *PROFILER.records[-1][1:]))
     return out
 
 

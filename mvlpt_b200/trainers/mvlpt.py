@@ -833,6 +833,45 @@ class CustomCLIP(nn.Module):
         return self.head(self.prompt_learner._emb.device).buffers(B, C)["logits"][:, :C]
 
 
+class LossSummary(dict):
+    """`forward_backward`'s return value: {"loss", "acc"[, "num_tasks"]} (trainers/mvlpt.py:940-946).  A dict whose loss
+    and accuracy are filled from the pinned host slot on first use (any read synchronises with the copy of ITS step,
+    not with the steps enqueued since), so a training loop that looks at the summary every few steps never stalls
+    the host in between.  The slot is reused after 16 further steps: read a summary before then (or keep `.resolve()`)."""
+
+    def __init__(self, host, event, extra):
+        super().__init__(loss=None, acc=None, **extra)
+        self._host, self._event = host, event
+
+    def resolve(self) -> "LossSummary":
+        if self._event is not None:
+            self._event.synchronize()
+            dict.__setitem__(self, "loss", float(self._host[0]))
+            dict.__setitem__(self, "acc", float(self._host[1]))
+            self._event = None
+        return self
+
+    def __getitem__(self, k):
+        return dict.__getitem__(self.resolve(), k)
+
+    def get(self, k, default=None):
+        return dict.get(self.resolve(), k, default)
+
+    def items(self):
+        return dict.items(self.resolve())
+
+    def values(self):
+        return dict.values(self.resolve())
+
+    def __repr__(self):
+        return dict.__repr__(self.resolve())
+
+    def __eq__(self, other):
+        return dict.__eq__(self.resolve(), other)
+
+    __hash__ = None
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Trainer (trainers/mvlpt.py:827-1125).  The reference subclasses Dassl's TrainerX; Dassl is not installable here,
 # so the handful of inherited members it uses (SURVEY.md App. F) are provided by this class itself.
@@ -914,7 +953,11 @@ class MVLPT:
         self.sched = R.build_lr_scheduler(self.optim, cfg.OPTIM)
         self.register_model("prompt_learner", self.model.prompt_learner, self.optim, self.sched)
         self.scaler = None  # amp: the kernels already scale gradients by a fixed power of two (engine.py)
-        self._metrics_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+        # loss / accuracy of a step travel to a ring of pinned host slots by asynchronous copies; the host only waits for
+        # one when somebody reads the summary (LossSummary), so it can enqueue the next steps meanwhile
+        self._metrics_host = torch.zeros(16, 2, dtype=torch.float32).pin_memory()
+        self._metrics_events = [torch.cuda.Event() for _ in range(16)]
+        self._metrics_slot = 0
 
     def forward_backward(self, batch):
         """trainers/mvlpt.py:910-951: forward, cross-entropy, backward, SGD step; returns the loss summary."""
@@ -926,14 +969,17 @@ class MVLPT:
         flat = model.grad_buffer()
         self.dp.all_reduce_sum(flat)
         self.optim.step(flat)
-        self._metrics_host.copy_(model.last_metrics(B), non_blocking=True)
-        torch.cuda.current_stream().synchronize()  # the reference's two .item() calls (:939-942)
-        loss_summary = {"loss": float(self._metrics_host[0]), "acc": float(self._metrics_host[1])}
-        if tasks_ is not None:
-            loss_summary.update({"num_tasks": len(set(tasks_.tolist()))})
+        slot = self._metrics_slot
+        self._metrics_slot = (slot + 1) % len(self._metrics_events)
+        host = self._metrics_host[slot]
+        host.copy_(model.last_metrics(B), non_blocking=True)  # the device -> host read of the step's result
+        self._metrics_events[slot].record(torch.cuda.current_stream(self.device))
+        extra = {"num_tasks": len(set(tasks_.tolist()))} if tasks_ is not None else {}
         if (self.batch_idx + 1) == self.num_batches:
             self.update_lr()
-        return loss_summary
+        # the reference's two .item() calls (:939-942) stall the host every step; here the summary waits for the copy when
+        # (and only when) it is read — Dassl prints it every TRAIN.PRINT_FREQ steps
+        return LossSummary(host, self._metrics_events[slot], extra)
 
     def _parse(self, batch):
         if self.cfg.DATASET.COOP:
