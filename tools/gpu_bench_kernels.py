@@ -64,6 +64,10 @@ if "gemm" in what:
         (7700, 1536, 512, 0, 0, 0, 0), (7700, 512, 512, 0, 1, 1, 0), (7700, 2048, 512, 1, 0, 0, 1),
         (7700, 512, 2048, 0, 1, 1, 0), (7700, 2048, 512, 2, 0, 0, 0), (7700, 512, 2048, 0, 0, 0, 0),
         (7700, 512, 512, 0, 0, 0, 0), (7700, 512, 1536, 0, 0, 0, 0), (77000, 2048, 512, 1, 0, 0, 1),
+        # small problems: the text tower at C=100 (M=2500), a 32-image shard (M=6560)      [18..]
+        (2500, 512, 2048, 0, 0, 0, 0), (2500, 512, 512, 0, 0, 0, 0), (2500, 512, 1536, 0, 0, 0, 0),
+        (2500, 2048, 512, 2, 0, 0, 0), (6560, 768, 3072, 0, 0, 0, 0), (6560, 768, 768, 0, 0, 0, 0),
+        (6560, 768, 2304, 0, 0, 0, 0), (6560, 3072, 768, 2, 0, 0, 0), (3750, 512, 2048, 0, 0, 0, 0),
     ]
     for (M, N, K, act, f32, resid, aux) in ([cases[0], cases[2], cases[6]] if ONE else ([cases[i] for i in only] if only else cases)):
         nb = 3
