@@ -276,6 +276,12 @@ typedef struct {
     int flip;           /* horizontal flip of the window                                                     */
 } mvlpt_image_desc;
 
+/* The tail of the same stack for a batch that already has the model's size (the workers cropped / resized, or the data is
+ * stored that way): uint8 [B, 3, H, W] -> ToTensor -> Normalize, bit-identical to torchvision (two IEEE divisions); out is
+ * [B, 3, H, W] fp16 (out_f16) or fp32.  H*W % 16 == 0.  Lets a loader ship 1 byte per value across PCIe instead of 2 or 4
+ * (the reference's loaders ship fp32 tensors, trainers/mvlpt.py:959-960). */
+int mvlpt_normalize_u8(const void* src, void* out, int out_f16, int B, int H, int W, const float* mean3, const float* std3,
+                       mvlpt_stream_t stream);
 size_t mvlpt_preprocess_workspace(const mvlpt_image_desc* descs_host, int B, int out_h, int out_w);
 int mvlpt_preprocess(const void* src, const mvlpt_image_desc* descs_host, const mvlpt_image_desc* descs_dev, int B,
                      const float* mean3, const float* std3, void* out, int out_f16, int out_h, int out_w, void* workspace,

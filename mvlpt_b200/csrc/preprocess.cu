@@ -234,9 +234,67 @@ int make_plan(const mvlpt_image_desc* h, int B, int out_h, int out_w, Plan& p, c
     return MVLPT_OK;
 }
 
+// ToTensor + Normalize of a batch that already has the model's size: uint8 [B, 3, H, W] -> (x / 255 - mean[c]) / std[c],
+// the same two IEEE divisions as above (a 256-entry table per channel in shared memory), 16 pixels per thread.
+template <typename T>
+__global__ void __launch_bounds__(256) normalize_u8_kernel(const uint4* __restrict__ src, T* __restrict__ out, Norm nm,
+                                                           int plane16, size_t total16) {
+    __shared__ float lut[3][256];
+    for (int i = threadIdx.x; i < 768; i += 256) {
+        const int c = i >> 8, px = i & 255;
+        lut[c][px] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)px, 255.f), nm.mean[c]), nm.std[c]);
+    }
+    __syncthreads();
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < total16; i += (size_t)gridDim.x * 256) {
+        const int c = (int)((i / plane16) % 3);
+        const uint4 v = __ldg(src + i);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        float f[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) f[k] = lut[c][(w[k >> 2] >> (8 * (k & 3))) & 255u];
+        if constexpr (sizeof(T) == 2) {
+            uint4 o[2];
+            uint32_t* po = reinterpret_cast<uint32_t*>(o);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+                const __half2 h = __floats2half2_rn(f[2 * k], f[2 * k + 1]);
+                po[k] = *reinterpret_cast<const uint32_t*>(&h);
+            }
+            reinterpret_cast<uint4*>(out)[2 * i] = o[0];
+            reinterpret_cast<uint4*>(out)[2 * i + 1] = o[1];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                reinterpret_cast<float4*>(out)[4 * i + k] = make_float4(f[4 * k], f[4 * k + 1], f[4 * k + 2], f[4 * k + 3]);
+        }
+    }
+}
+
 }  // namespace
 
 extern "C" {
+
+int mvlpt_normalize_u8(const void* src, void* out, int out_f16, int B, int H, int W, const float* mean3, const float* std3,
+                       mvlpt_stream_t stream) {
+    if (!src || !out || !mean3 || !std3) return fail(MVLPT_EINVAL, "mvlpt_normalize_u8: null argument");
+    if (B <= 0 || H <= 0 || W <= 0 || ((size_t)H * W) % 16)
+        return fail(MVLPT_ESHAPE, "mvlpt_normalize_u8: H*W must be a positive multiple of 16 (got %dx%d)", H, W);
+    if ((reinterpret_cast<uintptr_t>(src) | reinterpret_cast<uintptr_t>(out)) & 15)
+        return fail(MVLPT_EINVAL, "mvlpt_normalize_u8: src/out must be 16-byte aligned");
+    int rc = require_sm100();
+    if (rc) return rc;
+    Norm nm;
+    for (int c = 0; c < 3; ++c) { nm.mean[c] = mean3[c]; nm.std[c] = std3[c]; }
+    const int plane16 = H * W / 16;
+    const size_t total16 = (size_t)B * 3 * plane16;
+    const int grid = (int)((total16 + 255) / 256 < (size_t)sm_count() * 8 ? (total16 + 255) / 256 : (size_t)sm_count() * 8);
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (out_f16)
+        normalize_u8_kernel<__half><<<grid, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<__half*>(out), nm, plane16, total16);
+    else
+        normalize_u8_kernel<float><<<grid, 256, 0, s>>>(static_cast<const uint4*>(src), static_cast<float*>(out), nm, plane16, total16);
+    return launched("normalize_u8");
+}
 
 size_t mvlpt_preprocess_workspace(const mvlpt_image_desc* descs_host, int B, int out_h, int out_w) {
     Plan p;

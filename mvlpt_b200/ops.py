@@ -311,3 +311,14 @@ def pair_logits_bwd(dz16, ldc, img, txt, scale, d_txt, d_img, B, C, e):
 def cocoop_ctx_grad(dx16, ctx_pos, part_ws, d_ctx, d_bias, B, C, Lk, n_ctx, d, inv_scale):
     check(_lib.lib().mvlpt_cocoop_ctx_grad(_p(dx16), _p(ctx_pos), _p(part_ws), _p(d_ctx), _p(d_bias), B, C, Lk, n_ctx, d,
                                            float(inv_scale), _stream()), "mvlpt_cocoop_ctx_grad")
+
+
+def normalize_u8(src, out, mean, std):
+    """uint8 [B,3,H,W] -> ToTensor + Normalize -> out fp16 / fp32 [B,3,H,W] (mvlpt_normalize_u8)."""
+    import ctypes as C
+    B, _, H, W = src.shape
+    m = (C.c_float * 3)(*[float(x) for x in mean])
+    sd = (C.c_float * 3)(*[float(x) for x in std])
+    check(_lib.lib().mvlpt_normalize_u8(_p(src), _p(out), int(out.dtype == torch.float16), B, H, W, m, sd, _stream()),
+          "mvlpt_normalize_u8")
+    return out

@@ -998,28 +998,51 @@ class MVLPT:
         text tower first and only then waits for it, so the PCIe transfer hides behind compute; with `stage_batch` called
         one step ahead (run_epoch does) it hides behind the whole previous step.  Anything else takes the reference's plain
         `.to(device)` route (trainers/mvlpt.py:959-960)."""
+        u8 = input.dtype == torch.uint8
         if input.device.type != "cpu" or not input.is_pinned():
-            return input.to(self.device, non_blocking=True)
+            input = input.to(self.device, non_blocking=True)
+            return self._normalize_u8(input) if u8 else input
         key = (tuple(input.shape), input.dtype)
         if getattr(self, "_stage_key", None) != key:
             self._stage_key = key
             self._stage_bufs = [torch.empty(input.shape, dtype=input.dtype, device=self.device) for _ in range(2)]
+            self._stage_norm = [torch.empty(input.shape, dtype=self._image_dtype(), device=self.device) for _ in range(2)] \
+                if u8 else None
             self._stage_slot = 0
             self._copy_stream = torch.cuda.Stream(device=self.device)
         cs = self._copy_stream
-        buf = self._stage_bufs[self._stage_slot]
+        slot = self._stage_slot
+        buf = self._stage_bufs[slot]
         self._stage_slot ^= 1
         # everything enqueued so far — in particular the step that last read this buffer — is done before it is overwritten
         cs.wait_stream(torch.cuda.current_stream(self.device))
         with torch.cuda.stream(cs):
             buf.copy_(input, non_blocking=True)
+            if u8:  # one byte per value crossed PCIe; ToTensor + Normalize happen here, still on the copy stream
+                buf = self._normalize_u8(buf, self._stage_norm[slot])
             if label is not None and label.device.type == "cpu" and label.is_pinned():
-                label = label.to(self.device, non_blocking=True)
-                label.record_stream(torch.cuda.current_stream(self.device))
+                # into a persistent slot like the images: a fresh allocation per step on the copy stream makes the caching
+                # allocator grow (record_stream delays reuse) and every cudaMalloc it then needs stalls the device
+                lkey = (tuple(label.shape), label.dtype)
+                if getattr(self, "_stage_lkey", None) != lkey:
+                    self._stage_lkey = lkey
+                    self._stage_labels = [torch.empty(label.shape, dtype=label.dtype, device=self.device) for _ in range(2)]
+                label = self._stage_labels[slot].copy_(label, non_blocking=True)
             ev = torch.cuda.Event()
             ev.record(cs)
         buf._mvlpt_ready = ev
         return buf if label is None else (buf, label)
+
+    def _image_dtype(self):
+        return torch.float16 if self.cfg.TRAINER.MVLPT.PREC == "fp16" else torch.float32
+
+    def _normalize_u8(self, img_u8: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """uint8 [B,3,H,W] batches (images already at INPUT.SIZE: the loader kept them as bytes) -> ToTensor + Normalize with
+        INPUT.PIXEL_MEAN / PIXEL_STD on the device (`mvlpt_normalize_u8`, bit-identical to torchvision), on the current
+        stream.  The reference ships fp32 tensors from its CPU transform stack (trainers/mvlpt.py:959-960)."""
+        if out is None:
+            out = torch.empty(img_u8.shape, dtype=self._image_dtype(), device=img_u8.device)
+        return ops.normalize_u8(img_u8.contiguous(), out, self.cfg.INPUT.PIXEL_MEAN, self.cfg.INPUT.PIXEL_STD)
 
     def stage_batch(self, batch):
         """Start the host->device copies of a batch AHEAD of its step (pinned host tensors; anything else is returned as

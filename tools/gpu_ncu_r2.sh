@@ -4,7 +4,7 @@
 #   of the attention forward / backward kernels.
 set -u
 mkdir -p gpurun_out
-B="--steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-roofline --no-e2e"
+B="--steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-roofline --no-e2e --no-settle"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches_c3.csv \
     python bench.py --config 3 $B > gpurun_out/launches_c3.log 2>&1; echo "launch list config 3 exit $?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches_c2.csv \

@@ -37,5 +37,5 @@ ops.gemm(dt, w_fc.t().contiguous(), dh)                                         
 ops.gemm(dh, w_o.t().contiguous(), o)                                                     # dgrad out-proj
 ops.gemm(dqkv, w_qkv.t().contiguous(), dh)                                                # dgrad QKV
 torch.cuda.synchronize()
-json.dump(ops.GEMM_LOG, open("gpurun_out/gemm_order_shapes.json", "w"))
+json.dump(ops.GEMM_LOG, open(f"gpurun_out/gemm_order_shapes_{M}.json", "w"))
 print(len(ops.GEMM_LOG), "gemm launches logged")

@@ -31,10 +31,10 @@ if [[ $what == *configs* ]]; then
 fi
 if [[ $what == *launches* ]]; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches_vpt.csv \
-      python bench.py --mode vpt --steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-roofline --no-e2e > gpurun_out/launches_vpt.log 2>&1
+      python bench.py --mode vpt --steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-roofline --no-e2e --no-settle > gpurun_out/launches_vpt.log 2>&1
   echo "launch list vpt exit $?"
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 1400 --csv --log-file gpurun_out/launches_coop.csv \
-      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-roofline --no-e2e > gpurun_out/launches_coop.log 2>&1
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-eager-baseline --no-roofline --no-e2e --no-settle > gpurun_out/launches_coop.log 2>&1
   echo "launch list coop exit $?"
 fi
 if [[ $what == *ncu* ]]; then
