@@ -585,13 +585,9 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
 #pragma unroll
                     for (int q = 0; q < HC / 8; ++q) sgraw[q] = __ldg(reinterpret_cast<const uint4*>(ep.lnc_sg + c0) + q);
                 }
-                if (has_in) {
-                    mbar_wait(&in_full[slot], (uint32_t)(g / R) & 1);  // input landed (implies the slot was drained)
-                } else {
-                    // the slot about to be overwritten must have been drained by the TMA store of step g - R
-                    if (issuer) tma_store_wait_read_n(R - 1);
-                    gemm_bar_sync256();
-                }
+                // the slot about to be overwritten has been drained: with an epilogue input its arrival implies it; without,
+                // the issuer made sure of it BEFORE the barrier that ended the previous step (one barrier per step, not two)
+                if (has_in) mbar_wait(&in_full[slot], (uint32_t)(g / R) & 1);
                 uint8_t* orow = slab + row_off;
                 uint32_t raw[HC];
                 if constexpr (HC == 32) tmem_ld_32x32(t_row + s * SW, raw);
@@ -710,6 +706,9 @@ gemm_f16_tn_2sm_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_
                                        pack_h2(v[8 * u + 4], v[8 * u + 5]), pack_h2(v[8 * u + 6], v[8 * u + 7]));
                 }
                 fence_proxy_async_smem();
+                // the slot of step g+1 was last read by the store of step g+1-R: of the groups committed so far (up to
+                // g-1) all but the newest R-2 must have been read before anybody passes this barrier
+                if (!has_in && issuer) tma_store_wait_read_n(R - 2);
                 gemm_bar_sync256();
                 if (issuer) {
                     if (col0 < N) {
