@@ -95,6 +95,8 @@ def gemm(A, W, out, *, bias=None, act=ACT_NONE, aux_in=None, aux_out=None, resid
     d = GemmDesc(M, N, K, lda, ldw, ld_out, ld_aux, act, out_f32, float(alpha))
     t0 = PROFILER.begin() if PROFILER is not None else None
     tag = ",lnp=1" if ln_prod is not None else (",lnc=1" if ln_cons is not None else "")
+    if aux_out is not None:
+        tag += ",aux=1"  # the QuickGELU epilogue also stores the pre-activation
     key = f"gemm[M={M},N={N},K={K},act={act},f32={out_f32},resid={int(resid is not None)}{tag}]"
     if GEMM_LOG is not None:
         GEMM_LOG.append(key)
