@@ -31,6 +31,7 @@ from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import statistics
 import sys
@@ -457,6 +458,14 @@ def ncu_traffic_table():
     return d.get("shapes", {}), d.get("source")
 
 
+def settle_steps(dp, step_s, dev, target_s=1.2, cap=512):
+    """How many steps make up `target_s` seconds, THE SAME NUMBER ON EVERY RANK: the slowest rank's measured seconds per
+    step is taken (max all-reduce) and every rank derives the count from that one value."""
+    t = torch.tensor([float(step_s)], device=dev, dtype=torch.float64)
+    dp.all_reduce_max(t)
+    return max(0, min(cap, int(math.ceil(target_s / max(float(t), 1e-4)))))
+
+
 def ours_arm(a):
     from mvlpt_b200 import _lib, ops
     from mvlpt_b200.trainers.mvlpt import MVLPT
@@ -540,15 +549,20 @@ def ours_arm(a):
     torch.cuda.synchronize()
     # thermal settle: a B200 under its 1 kW cap sheds ~5 % of its clocks over the first second of sustained load; the timed
     # regions below (device-resident, end to end, instrumented) run back to back, so the first one would otherwise see a
-    # cooler chip than the others.  Extra warm-up steps (never fewer than --warmup) until ~1.2 s of steps have run.
-    t0 = time.perf_counter()
-    settle = 0
-    while time.perf_counter() - t0 < 1.2 and not a.no_settle:
-        step(dev_batches[settle % nbuf])
-        settle += 1
-        if settle % 8 == 0:
-            torch.cuda.synchronize()
-    torch.cuda.synchronize()
+    # cooler chip than the others.  Extra warm-up steps (never fewer than --warmup) worth ~1.2 s of steps.  Their NUMBER
+    # is agreed across ranks (settle_steps): every training step issues a gradient all-reduce, so ranks that each ran
+    # "until 1.2 s have passed" on their own clocks would issue different numbers of collectives and deadlock.
+    if not a.no_settle:
+        probe = 4
+        t0 = time.perf_counter()
+        for i in range(probe):
+            step(dev_batches[i % nbuf])
+        torch.cuda.synchronize()
+        for i in range(settle_steps(dp, (time.perf_counter() - t0) / probe, dev) - probe):
+            step(dev_batches[i % nbuf])
+            if i % 8 == 7:
+                torch.cuda.synchronize()
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     sampler.start()

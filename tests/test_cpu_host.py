@@ -152,6 +152,14 @@ assert torch.allclose(mine, full, atol=1e-6)
 t = torch.tensor([float(dp.rank + 1)], dtype=torch.float64)
 dp.all_reduce_max(t)
 assert float(t) == 2.0
+# bench.py's thermal-settle count: ranks that measured different step times must still run the SAME number of steps
+# (each step issues a gradient all-reduce; a count taken from a rank's own clock deadlocks the job)
+import bench
+n = bench.settle_steps(dp, 0.010 * (dp.rank + 1), torch.device("cpu"))
+agreed = torch.tensor([float(n), -float(n)], dtype=torch.float64)
+dp.all_reduce_max(agreed)
+assert n == 60 and agreed.tolist() == [60.0, -60.0], (n, agreed)
+assert bench.settle_steps(dp, 1e-9, torch.device("cpu")) == 512 and bench.settle_steps(dp, 5.0, torch.device("cpu")) == 1
 # class-sharded text tower (SURVEY.md 8e): per-rank class ranges tile [0, C); padded all-gather of the features;
 # reduce-scatter of their gradients gives every rank the SUM over ranks for its own classes
 C, e = 7, 3
