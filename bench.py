@@ -552,13 +552,15 @@ def ours_arm(a):
     # cooler chip than the others.  Extra warm-up steps (never fewer than --warmup) worth ~1.2 s of steps.  Their NUMBER
     # is agreed across ranks (settle_steps): every training step issues a gradient all-reduce, so ranks that each ran
     # "until 1.2 s have passed" on their own clocks would issue different numbers of collectives and deadlock.
+    settle = 0
     if not a.no_settle:
         probe = 4
         t0 = time.perf_counter()
         for i in range(probe):
             step(dev_batches[i % nbuf])
         torch.cuda.synchronize()
-        for i in range(settle_steps(dp, (time.perf_counter() - t0) / probe, dev) - probe):
+        settle = max(probe, settle_steps(dp, (time.perf_counter() - t0) / probe, dev))
+        for i in range(settle - probe):
             step(dev_batches[i % nbuf])
             if i % 8 == 7:
                 torch.cuda.synchronize()

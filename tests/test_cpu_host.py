@@ -279,3 +279,9 @@ def test_cli_reads_the_reference_yaml_unchanged():
     assert c.OPTIM.LR == 0.002 and c.OPTIM.MAX_EPOCH == 200 and c.OPTIM.WARMUP_CONS_LR == 1e-5
     assert c.DATALOADER.TRAIN_X.BATCH_SIZE == 32 and c.DATALOADER.TEST.BATCH_SIZE == 100
     assert c.TRAINER.MVLPT.COOP.CSC is False and c.TEST.NO_TEST is False and c.TRAINER.CUT_CONTEXTLEN is True
+
+
+def test_no_undefined_names_in_gpu_only_code():
+    """bench.py's GPU arm and the trainers cannot execute without a GPU; a scope-aware check keeps NameErrors out of them."""
+    r = subprocess.run([sys.executable, str(REPO / "tools" / "lint_names.py")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
