@@ -91,6 +91,8 @@ def parse_args():
     ap.add_argument("--no-roofline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-settle", action="store_true", help="skip the ~1.2 s of extra warm-up steps (profiler runs)")
+    ap.add_argument("--watchdog-s", type=float, default=1500.0,
+                    help="GPU arm: abort the process (exit 124) if no result line after this many seconds; 0 = off")
     ap.add_argument("--gemm-log", default="", help="write the ordered shape keys of every GEMM launch of the process to "
                                                    "this JSON file (tools/ncu_traffic.py matches an ncu capture to it)")
     ap.add_argument("--eval", action="store_true",
@@ -458,6 +460,22 @@ def ncu_traffic_table():
     return d.get("shapes", {}), d.get("source")
 
 
+def arm_watchdog(seconds):
+    """Bound a hung run: ranks stuck in a mismatched collective spin on their GPUs until the CALLER's limit expires (that is
+    how the round's last 8-GPU session was lost).  A daemon timer ends this process instead; a finished run never sees it."""
+    if seconds <= 0:
+        return
+
+    def fire():
+        sys.stderr.write(f"bench.py: watchdog: no result line after {seconds:g} s, aborting (exit 124)\n")
+        sys.stderr.flush()
+        os._exit(124)
+
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
+
+
 def settle_steps(dp, step_s, dev, target_s=1.2, cap=512):
     """How many steps make up `target_s` seconds, THE SAME NUMBER ON EVERY RANK: the slowest rank's measured seconds per
     step is taken (max all-reduce) and every rank derives the count from that one value."""
@@ -472,6 +490,7 @@ def ours_arm(a):
     from mvlpt_b200.trainers.runtime import DataParallelGroup
     from mvlpt_b200.accounting import flops_step, text_flops
 
+    arm_watchdog(a.watchdog_s)
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

@@ -285,3 +285,14 @@ def test_no_undefined_names_in_gpu_only_code():
     """bench.py's GPU arm and the trainers cannot execute without a GPU; a scope-aware check keeps NameErrors out of them."""
     r = subprocess.run([sys.executable, str(REPO / "tools" / "lint_names.py")], capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout
+
+
+def test_bench_watchdog_ends_a_hung_run():
+    """A rank stuck in a collective must not hold its GPU until the caller's limit: the watchdog exits 124; a finished run
+    is not affected."""
+    code = "import bench, time; bench.arm_watchdog(0.3); time.sleep(20); print('not reached')"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=120, cwd=str(REPO))
+    assert r.returncode == 124 and "watchdog" in r.stderr and "not reached" not in r.stdout
+    r = subprocess.run([sys.executable, "-c", "import bench; bench.arm_watchdog(60); print('done')"],
+                       capture_output=True, text=True, timeout=120, cwd=str(REPO))
+    assert r.returncode == 0 and "done" in r.stdout
