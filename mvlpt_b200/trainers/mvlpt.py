@@ -860,6 +860,15 @@ class LossSummary(dict):
     def items(self):
         return dict.items(self.resolve())
 
+    def keys(self):
+        return dict.keys(self.resolve())
+
+    def __iter__(self):  # also takes dict(summary) / {**summary} off CPython's raw-table fast path, which would copy None
+        return dict.__iter__(self.resolve())
+
+    def copy(self):
+        return dict(dict.items(self.resolve()))
+
     def values(self):
         return dict.values(self.resolve())
 

@@ -296,3 +296,30 @@ def test_bench_watchdog_ends_a_hung_run():
     r = subprocess.run([sys.executable, "-c", "import bench; bench.arm_watchdog(60); print('done')"],
                        capture_output=True, text=True, timeout=120, cwd=str(REPO))
     assert r.returncode == 0 and "done" in r.stdout
+
+
+def test_loss_summary_reads_lazily_and_survives_every_way_of_copying_a_dict():
+    """forward_backward's return value (trainers/mvlpt.py:940-946 keys) waits for ITS step's copy on first use only, and
+    dict(summary) / {**summary} / json / MetricMeter-style update all see the numbers, never the unread placeholders."""
+    import json
+    import torch
+    from mvlpt_b200.trainers.mvlpt import LossSummary
+
+    class Event:
+        waits = 0
+
+        def synchronize(self):
+            Event.waits += 1
+
+    host = torch.tensor([1.5, 75.0])
+    want = {"loss": 1.5, "acc": 75.0, "num_tasks": 3}
+    mk = lambda: LossSummary(host, Event(), {"num_tasks": 3})  # noqa: E731
+    s = mk()
+    assert Event.waits == 0 and "loss" in s and len(s) == 3 and Event.waits == 0   # nothing read yet
+    assert s["loss"] == 1.5 and s["acc"] == 75.0 and Event.waits == 1 and s.get("num_tasks") == 3 and Event.waits == 1
+    for copy in (dict(mk()), {**mk()}, mk().copy(), json.loads(json.dumps(mk())), dict(mk().items()),
+                 {k: mk()[k] for k in mk()}):
+        assert copy == want
+    meter = {}
+    meter.update(mk())
+    assert meter == want and mk() == want and list(mk().keys()) == list(want) and list(mk().values()) == list(want.values())
