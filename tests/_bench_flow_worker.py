@@ -81,6 +81,13 @@ class StubTrainer:
     def stage_batch(self, batch):
         return batch
 
+    def parse_batch_test(self, batch):
+        return batch["img"], batch["label"], batch["domain"]
+
+    def model_inference(self, image, task=None):
+        StubTrainer.steps += 1
+        return torch.zeros(image.shape[0], 16)
+
     def forward_backward(self, batch):
         StubTrainer.steps += 1
         time.sleep(0.002 * (1 + self.dp.rank))  # ranks run at different speeds: their own clocks disagree

@@ -55,3 +55,9 @@ def test_gpu_arm_control_flow_strong_scaling_two_ranks():
     line = json.loads([ln for o, _ in outs for ln in o.splitlines() if ln.startswith("{")][0])
     assert line["scaling"] == "strong" and line["config"]["global_batch"] == 4 and line["config"]["thermal_settle_steps"] == 0
     assert len({_steps(e) for _, e in outs}) == 1
+
+
+def test_gpu_arm_control_flow_eval():
+    outs = _run(1, 29657, extra=("--eval",))
+    line = json.loads([ln for o, _ in outs for ln in o.splitlines() if ln.startswith("{")][0])
+    assert line["metric"].startswith("inference images/sec") and line["value"] > 0 and line["cpu_baseline"] is None
