@@ -904,6 +904,10 @@ class MVLPT:
         if device is None:
             raise ops._lib.MvlptError("MVLPT trainer needs a CUDA device (sm_100a); there is no CPU path")
         self.device = torch.device(device)
+        if self.device.type == "cuda" and self.device.index is not None \
+                and self.device.index != torch.cuda.current_device():
+            # the library launches on the CURRENT device, on its current stream (ops._stream): one process drives one GPU
+            torch.cuda.set_device(self.device)
         self.dp = dp if dp is not None else R.DataParallelGroup()
         self._models, self._optims, self._scheds = OrderedDict(), OrderedDict(), OrderedDict()
         self.epoch, self.start_epoch = 0, 0
